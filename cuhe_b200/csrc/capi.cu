@@ -1,0 +1,738 @@
+// cuhe_b200/csrc/capi.cu -- context, table construction and the extern "C"
+// entry points declared in include/cuhe_b200.h.
+//
+// Host-side counterpart of cuhe/CuHE.cu:36-78 (init), cuhe/Operations.cu
+// (precompute + launch wrappers), cuhe/Relinearization.cu and
+// cuhe/DeviceManager.cu.  State that the reference keeps in file-scope globals
+// (param, crtPrime, icrtConst, d_swap, d_hold, d_barrett_*, d_relin, h_ek) is
+// owned by an explicit context; every temporary is stream-ordered pool memory,
+// so concurrent streams on one device are safe (the reference's singleton
+// scratch is not).
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/cuhe_b200.h"
+#include "engine.hpp"
+#include "host_math.hpp"
+#include "rns.cuh"
+
+namespace cuhe_b200 {
+
+static thread_local std::string g_err;
+static thread_local long long g_launches = 0;
+void count_launch() { g_launches++; }
+
+struct CudaFail {
+    cudaError_t e; const char* what; int line;
+};
+#define CK(call)                                                           \
+    do {                                                                   \
+        cudaError_t _e = (call);                                           \
+        if (_e != cudaSuccess) throw CudaFail{_e, #call, __LINE__};        \
+    } while (0)
+
+struct ArgError { std::string msg; };
+struct StateError { std::string msg; };
+#define REQUIRE(cond, msg) do { if (!(cond)) throw ArgError{std::string(msg)}; } while (0)
+
+// twiddle tables of one transform length
+struct NttPlan {
+    int N = 0, n2 = 0, r3 = 0;
+    uint64_t* tw1 = nullptr;    // [64][n2]  w^(k1*j2)
+    uint64_t* tw1s = nullptr;   // [64][n2]  N^-1 * w^(k1*j2)
+    uint64_t* tw2 = nullptr;    // [64][r3]  w^(64*k2a*j2b)
+};
+
+struct IcrtDev { uint32_t *M = nullptr, *mi = nullptr, *bi = nullptr; int L = 0, W = 0, Wp = 0; };
+
+}  // namespace cuhe_b200
+
+using namespace cuhe_b200;
+
+struct cuhe_ctx {
+    hm::Params par;
+    int device = 0, rank = 0, world = 1;
+    cudaMemPool_t pool = nullptr;
+    std::vector<uint32_t> primes;
+    std::vector<hm::Big> moduli;
+    // device tables
+    uint32_t* d_primes = nullptr;
+    uint64_t* d_mus = nullptr;
+    uint32_t* d_pow32 = nullptr; int pow_stride = 0;
+    uint32_t* d_invp = nullptr;
+    std::vector<IcrtDev> icrt;
+    std::map<int, NttPlan> plans;
+    // Barrett tables for the local rows of level 0
+    bool have_polymod = false;
+    uint64_t *d_u_ntt = nullptr, *d_m_ntt = nullptr;
+    uint32_t* d_m_crt = nullptr;
+    // relinearization keys: [rows(0)][numEvalKey][N]
+    uint64_t* d_ek = nullptr;
+    std::mutex mu;
+
+    int L(int lvl) const { return par.numCrtPrimeAt(lvl); }
+    int rows(int lvl) const { int l = L(lvl); return rank < l ? (l - rank + world - 1) / world : 0; }
+    PrimeView pv() const { return PrimeView{d_primes, d_mus, rank, world}; }
+};
+
+namespace cuhe_b200 {
+
+static void* pool_alloc(cuhe_ctx* c, size_t bytes, cudaStream_t st) {
+    void* p = nullptr;
+    if (bytes == 0) bytes = 16;
+    CK(cudaMallocFromPoolAsync(&p, bytes, c->pool, st));
+    return p;
+}
+static void pool_free(void* p, cudaStream_t st) { if (p) CK(cudaFreeAsync(p, st)); }
+// RAII stream-ordered temporary
+struct Tmp {
+    void* p = nullptr; cudaStream_t st;
+    Tmp(cuhe_ctx* c, size_t bytes, cudaStream_t s) : st(s) { p = pool_alloc(c, bytes, s); }
+    ~Tmp() { if (p) cudaFreeAsync(p, st); }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+template <class T>
+static T* upload(const std::vector<T>& v) {
+    T* d = nullptr;
+    CK(cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(T)));
+    if (!v.empty()) CK(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return d;
+}
+
+// roots[i] = w0^i, w0 = g^(65536/N)  (cuhe/Base.cu:64-69) and the derived pass tables
+static const NttPlan& get_plan(cuhe_ctx* c, int N) {
+    std::lock_guard<std::mutex> lk(c->mu);
+    auto it = c->plans.find(N);
+    if (it != c->plans.end()) return it->second;
+    REQUIRE(N == 16384 || N == 32768 || N == 65536, "NTT length must be 16384, 32768 or 65536");
+    NttPlan pl;
+    pl.N = N; pl.n2 = N / 64; pl.r3 = pl.n2 / 64;
+    std::vector<uint64_t> roots(N);
+    const uint64_t w0 = hm::powP(hm::G, (uint64_t)(65536 / N));
+    roots[0] = 1;
+    for (int i = 1; i < N; i++) roots[i] = hm::mulP(roots[i - 1], w0);
+    const uint64_t ninv = hm::powP((uint64_t)N, hm::P - 2);
+    std::vector<uint64_t> tw1((size_t)N), tw1s((size_t)N), tw2((size_t)pl.n2);
+    for (int k1 = 0; k1 < 64; k1++)
+        for (int j2 = 0; j2 < pl.n2; j2++) {
+            uint64_t w = roots[((long long)k1 * j2) & (N - 1)];
+            tw1[(size_t)k1 * pl.n2 + j2] = w;
+            tw1s[(size_t)k1 * pl.n2 + j2] = hm::mulP(w, ninv);
+        }
+    for (int k2a = 0; k2a < 64; k2a++)
+        for (int j2b = 0; j2b < pl.r3; j2b++)
+            tw2[(size_t)k2a * pl.r3 + j2b] = roots[(64ll * k2a * j2b) & (N - 1)];
+    pl.tw1 = upload(tw1); pl.tw1s = upload(tw1s); pl.tw2 = upload(tw2);
+    return c->plans.emplace(N, pl).first->second;
+}
+
+// ---- transform drivers -------------------------------------------------------
+// forward zero-padded transform of `count` polynomials.
+//   src: u32, polynomial t at src + t*src_stride (+ offset), crtLen = N/2 words read
+//   mul_tab != null: outputs multiplied by mul_tab[t % row_mod][.]
+static void fwd_ntt(cuhe_ctx* c, int N, uint64_t* dst, const uint32_t* src, long long src_stride, int count,
+                    const uint64_t* mul_tab, int row_mod, cudaStream_t st) {
+    const NttPlan& pl = get_plan(c, N);
+    Tmp scratch(c, (size_t)count * N * 8, st);
+    Pass1Args a{};
+    a.scratch = scratch.as<uint64_t>(); a.src = src; a.tw1 = pl.tw1; a.src_stride = src_stride; a.n2 = pl.n2;
+    CK(launch_pass1(IN_EXT_U32, a, count, st));
+    Pass2Args b{};
+    b.dst = dst; b.scratch = scratch.as<uint64_t>(); b.tw2 = pl.tw2; b.mul_tab = mul_tab; b.dst_stride = N;
+    b.row_mod = row_mod > 0 ? row_mod : 1;
+    CK(launch_pass2(pl.r3, mul_tab ? OUT_U64_MUL : OUT_U64, b, count, st));
+}
+// inverse transform + % p of `count` = k*rows transforms -> u32[count][N] (all outputs)
+static void inv_ntt_modp(cuhe_ctx* c, int N, uint32_t* dst, const uint64_t* src, const uint64_t* src2, int count,
+                         int row_mod, cudaStream_t st) {
+    const NttPlan& pl = get_plan(c, N);
+    Tmp scratch(c, (size_t)count * N * 8, st);
+    Pass1Args a{};
+    a.scratch = scratch.as<uint64_t>(); a.src = src; a.src2 = src2; a.tw1 = pl.tw1s;
+    a.src_stride = N; a.src2_stride = N; a.n2 = pl.n2;
+    CK(launch_pass1(src2 ? IN_U64_REV_MUL : IN_U64_REV, a, count, st));
+    Pass2Args b{};
+    b.dst = dst; b.scratch = scratch.as<uint64_t>(); b.tw2 = pl.tw2; b.primes = c->d_primes; b.mus = c->d_mus;
+    b.dst_stride = N; b.prime_base = c->rank; b.prime_step = c->world; b.row_mod = row_mod > 0 ? row_mod : 1;
+    CK(launch_pass2(pl.r3, OUT_U32_MODP, b, count, st));
+}
+
+static void barrett_impl(cuhe_ctx* c, uint32_t* dst, const uint32_t* hold, int lvl, cudaStream_t st) {
+    if (!c->have_polymod) throw StateError{"Barrett reduction needs cuhe_ctx_set_poly_modulus_host first"};
+    const int N = c->par.nttLen, H = c->par.crtLen, n = c->par.modLen, rows = c->rows(lvl);
+    if (rows == 0) return;
+    Tmp g(c, (size_t)rows * N * 8, st), t(c, (size_t)rows * N * 4, st), s(c, (size_t)rows * N * 4, st);
+    // g = NTT(f >> (n-1)) * NTT(u)        (cuhe/Operations.cu:469-474)
+    fwd_ntt(c, N, g.as<uint64_t>(), hold + (n - 1), N, rows, c->d_u_ntt, rows, st);
+    // t = INTT(g) % p                      (:475)
+    inv_ntt_modp(c, N, t.as<uint32_t>(), g.as<uint64_t>(), nullptr, rows, rows, st);
+    // g = NTT(t >> n) * NTT(m')            (:478-485)
+    fwd_ntt(c, N, g.as<uint64_t>(), t.as<uint32_t>() + n, N, rows, c->d_m_ntt, rows, st);
+    // s = INTT(g) % p                      (:489)
+    inv_ntt_modp(c, N, s.as<uint32_t>(), g.as<uint64_t>(), nullptr, rows, rows, st);
+    // out = f - (t on [n,2n)) - s, conditional -m'   (:486-500)
+    dim3 grid((H + 255) / 256, rows);
+    barrett_finish_kernel<<<grid, 256, 0, st>>>(dst, hold, t.as<uint32_t>(), s.as<uint32_t>(), c->d_m_crt, c->pv(), n,
+                                               H, N);
+    count_launch();
+    CK(cudaGetLastError());
+}
+
+__global__ void take_low_half_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, int H, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < H) dst[(long long)blockIdx.y * H + i] = src[(long long)blockIdx.y * N + i];
+}
+// residues of small signed coefficients: out[r][i] = coeffs[i] mod p_(r)
+__global__ void small_poly_crt_kernel(uint32_t* __restrict__ out, const long long* __restrict__ coeffs, int ncoef,
+                                      PrimeView pv, int H) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (i >= H) return;
+    uint32_t v = 0;
+    if (i < ncoef) {
+        const long long p = pv.p[pv.base + pv.step * r];
+        long long t = coeffs[i] % p;
+        if (t < 0) t += p;
+        v = (uint32_t)t;
+    }
+    out[(long long)r * H + i] = v;
+}
+
+// ---- mod-P primitives on arrays (the harness of tests/test_ModP.cu) -------------
+template <int S>
+__device__ __forceinline__ uint64_t shl_dispatch(uint64_t x, int s) {
+    if constexpr (S >= 192) return x;
+    else { if (s == S) return shl_modP<S>(x); return shl_dispatch<S + 1>(x, s); }
+}
+__global__ void modp_batch_kernel(int op, uint64_t* __restrict__ out, const uint64_t* __restrict__ x,
+                                  const uint64_t* __restrict__ y, size_t n, int shift) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t a = x[i], r;
+    if (op == 0) r = add_modP(a, y[i]);
+    else if (op == 1) r = sub_modP(a, y[i]);
+    else if (op == 2) r = mul_modP(a, y[i]);
+    else r = shl_dispatch<0>(a, shift);
+    out[i] = r;
+}
+
+template <int WMAX>
+static void launch_icrt(uint32_t* dst, const uint32_t* src, cuhe_ctx* c, const IcrtDev& ic, int b, int e, cudaStream_t st) {
+    const int cnt = e - b;
+    icrt_kernel<WMAX><<<(cnt + 127) / 128, 128, 0, st>>>(dst, src, c->d_primes, c->d_mus, ic.M, ic.mi, ic.bi, ic.L, ic.W,
+                                                         ic.Wp, b, e, c->par.crtLen);
+    count_launch();
+}
+
+}  // namespace cuhe_b200
+
+// ============================================================================
+// extern "C"
+// ============================================================================
+namespace cuhe_b200 {
+static int guarded(const std::function<void()>& f) {
+    try {
+        f();
+        return CUHE_OK;
+    } catch (const CudaFail& e) {
+        char buf[512];
+        snprintf(buf, sizeof buf, "CUDA error %d (%s) at capi.cu:%d: %s", (int)e.e, cudaGetErrorString(e.e), e.line, e.what);
+        g_err = buf;
+        return CUHE_ERR_CUDA;
+    } catch (const ArgError& e) {
+        g_err = e.msg; return CUHE_ERR_ARG;
+    } catch (const StateError& e) {
+        g_err = e.msg; return CUHE_ERR_STATE;
+    } catch (const std::invalid_argument& e) {
+        g_err = e.what(); return CUHE_ERR_ARG;
+    } catch (const std::bad_alloc&) {
+        g_err = "host allocation failed"; return CUHE_ERR_ALLOC;
+    } catch (const std::exception& e) {
+        g_err = e.what(); return CUHE_ERR_ARG;
+    }
+}
+static void to_c(const hm::Params& q, cuhe_params* o) {
+    o->mSize = q.mSize; o->modLen = q.modLen; o->modLen2 = q.modLen2; o->rawLen = q.rawLen; o->crtLen = q.crtLen;
+    o->nttLen = q.nttLen; o->logCoeffMax = q.logCoeffMax; o->logCoeffMin = q.logCoeffMin; o->logCoeffCut = q.logCoeffCut;
+    o->depth = q.depth; o->modMsg = q.modMsg; o->logMsg = q.logMsg; o->wordsMsg = q.wordsMsg; o->logRelin = q.logRelin;
+    o->numEvalKey = q.numEvalKey; o->logCrtPrime = q.logCrtPrime; o->numCrtPrime = q.numCrtPrime;
+}
+static hm::Params from_c(const cuhe_params* o) {
+    hm::Params q;
+    q.mSize = o->mSize; q.modLen = o->modLen; q.modLen2 = o->modLen2; q.rawLen = o->rawLen; q.crtLen = o->crtLen;
+    q.nttLen = o->nttLen; q.logCoeffMax = o->logCoeffMax; q.logCoeffMin = o->logCoeffMin; q.logCoeffCut = o->logCoeffCut;
+    q.depth = o->depth; q.modMsg = o->modMsg; q.logMsg = o->logMsg; q.wordsMsg = o->wordsMsg; q.logRelin = o->logRelin;
+    q.numEvalKey = o->numEvalKey; q.logCrtPrime = o->logCrtPrime; q.numCrtPrime = o->numCrtPrime;
+    return q;
+}
+struct DeviceGuard {
+    int prev = 0;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+static void check_lvl(const cuhe_ctx* c, int lvl) {
+    REQUIRE(c != nullptr, "null context");
+    REQUIRE(lvl >= 0 && lvl < c->par.depth, "level out of range");
+}
+}  // namespace cuhe_b200
+
+extern "C" {
+
+int cuhe_version(void) { return 100; }
+const char* cuhe_last_error(void) { return g_err.c_str(); }
+long long cuhe_launch_count(int reset) { long long v = g_launches; if (reset) g_launches = 0; return v; }
+
+int cuhe_set_parameters(cuhe_params* out, int d, int p, int w, int mn, int cut, int m) {
+    return guarded([&] {
+        REQUIRE(out != nullptr, "null output");
+        hm::Params q = hm::set_param(d, p, w, mn, cut, m);
+        REQUIRE(q.nttLen == 16384 || q.nttLen == 32768 || q.nttLen == 65536,
+                "ring degree unsupported: nttLen must be 16384, 32768 or 65536 (cuhe/Base.cu:58-62)");
+        to_c(q, out);
+    });
+}
+#define PARAM_GETTER(name, expr)                                               \
+    int name(const cuhe_params* p, int v) {                                    \
+        int r = -1;                                                            \
+        int rc = guarded([&] { REQUIRE(p != nullptr, "null params"); hm::Params q = from_c(p); r = (expr); }); \
+        return rc == CUHE_OK ? r : -rc;                                        \
+    }
+PARAM_GETTER(cuhe_param_num_crt_prime, q.numCrtPrimeAt(v))
+PARAM_GETTER(cuhe_param_log_coeff, q.logCoeffAt(v))
+PARAM_GETTER(cuhe_param_words_coeff, q.wordsCoeffAt(v))
+PARAM_GETTER(cuhe_param_num_eval_key, q.numEvalKeyAt(v))
+int cuhe_param_get_level(const cuhe_params* p, int logq) {
+    if (!p) return -CUHE_ERR_ARG;
+    return from_c(p).levelOf(logq);
+}
+
+int cuhe_ctx_create(cuhe_ctx** out, const cuhe_params* p, int device, int shard_rank, int shard_world) {
+    return guarded([&] {
+        REQUIRE(out && p, "null argument");
+        REQUIRE(shard_world >= 1 && shard_rank >= 0 && shard_rank < shard_world, "bad shard");
+        int ndev = 0;
+        CK(cudaGetDeviceCount(&ndev));
+        REQUIRE(device >= 0 && device < ndev, "no such CUDA device");
+        std::unique_ptr<cuhe_ctx> c(new cuhe_ctx);
+        c->par = from_c(p);
+        // re-derive and compare so a hand-edited struct cannot desynchronise sizes
+        hm::Params chk = hm::set_param(p->depth, p->modMsg, p->logRelin, p->logCoeffMin, p->logCoeffCut, p->mSize);
+        REQUIRE(chk.nttLen == p->nttLen && chk.numCrtPrime == p->numCrtPrime && chk.modLen == p->modLen &&
+                    chk.logCrtPrime == p->logCrtPrime && chk.numEvalKey == p->numEvalKey,
+                "cuhe_params was not produced by cuhe_set_parameters");
+        c->device = device; c->rank = shard_rank; c->world = shard_world;
+        DeviceGuard dg(device);
+        // pool: replaces DeviceAllocator (cuhe/DeviceManager.cu:36-138)
+        cudaMemPoolProps props{};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        CK(cudaMemPoolCreate(&c->pool, &props));
+        uint64_t thr = UINT64_MAX;
+        CK(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        // CRT tables (cuhe/Operations.cu:37-160)
+        c->primes = hm::gen_crt_primes(c->par);
+        for (uint32_t pr : c->primes) REQUIRE(pr < (1u << 26), "CRT primes must be below 2^26");
+        // no-wrap bound of the NTT-based convolution: n*(p-1)^2 < P (cuhe/Parameters.cu:78)
+        {
+            hm::u128 worst = (hm::u128)c->par.modLen * (hm::u128)(c->primes[0] - 1) * (c->primes[0] - 1);
+            REQUIRE(worst < (hm::u128)hm::P, "CRT primes too large for this ring degree");
+        }
+        c->moduli = hm::gen_coeff_moduli(c->par, c->primes);
+        c->d_primes = upload(c->primes);
+        std::vector<uint64_t> mus(c->primes.size());
+        for (size_t i = 0; i < mus.size(); i++) mus[i] = (uint64_t)(((hm::u128)1 << 64) / c->primes[i]);
+        c->d_mus = upload(mus);
+        c->pow_stride = c->par.wordsCoeffAt(0) + 1;
+        std::vector<uint32_t> pw(c->primes.size() * (size_t)c->pow_stride);
+        for (size_t l = 0; l < c->primes.size(); l++) {
+            uint64_t v = 1 % c->primes[l], b = ((uint64_t)1 << 32) % c->primes[l];
+            for (int k = 0; k < c->pow_stride; k++) { pw[l * c->pow_stride + k] = (uint32_t)v; v = v * b % c->primes[l]; }
+        }
+        c->d_pow32 = upload(pw);
+        c->d_invp = upload(hm::gen_crt_inv_primes(c->primes));
+        c->icrt.resize(c->par.depth);
+        for (int lvl = 0; lvl < c->par.depth; lvl++) {
+            hm::IcrtConst ic = hm::gen_icrt(c->par, c->primes, c->moduli, lvl);
+            IcrtDev d;
+            d.L = ic.L; d.W = ic.W; d.Wp = ic.Wp;
+            d.M = upload(ic.M); d.mi = upload(ic.mi); d.bi = upload(ic.bi);
+            c->icrt[lvl] = d;
+        }
+        CK(cudaFuncSetAttribute(crt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        get_plan(c.get(), c->par.nttLen);
+        CK(cudaDeviceSynchronize());
+        *out = c.release();
+    });
+}
+
+int cuhe_ctx_destroy(cuhe_ctx* c) {
+    return guarded([&] {
+        if (!c) return;
+        DeviceGuard dg(c->device);
+        cudaDeviceSynchronize();
+        for (auto& kv : c->plans) { cudaFree(kv.second.tw1); cudaFree(kv.second.tw1s); cudaFree(kv.second.tw2); }
+        for (auto& d : c->icrt) { cudaFree(d.M); cudaFree(d.mi); cudaFree(d.bi); }
+        cudaFree(c->d_primes); cudaFree(c->d_mus); cudaFree(c->d_pow32); cudaFree(c->d_invp);
+        cudaFree(c->d_u_ntt); cudaFree(c->d_m_ntt); cudaFree(c->d_m_crt); cudaFree(c->d_ek);
+        if (c->pool) cudaMemPoolDestroy(c->pool);
+        delete c;
+    });
+}
+int cuhe_ctx_params(const cuhe_ctx* c, cuhe_params* out) {
+    return guarded([&] { REQUIRE(c && out, "null argument"); to_c(c->par, out); });
+}
+int cuhe_ctx_crt_primes_host(const cuhe_ctx* c, uint32_t* out) {
+    return guarded([&] { REQUIRE(c && out, "null argument"); memcpy(out, c->primes.data(), c->primes.size() * 4); });
+}
+int cuhe_ctx_coeff_modulus_host(const cuhe_ctx* c, int lvl, uint32_t* words, int nwords) {
+    return guarded([&] {
+        check_lvl(c, lvl);
+        REQUIRE(words && nwords >= (int)c->moduli[lvl].size(), "word buffer too small");
+        hm::big_to_words(c->moduli[lvl], words, nwords);
+    });
+}
+int cuhe_ctx_rows(const cuhe_ctx* c, int lvl) {
+    int r = -1;
+    int rc = guarded([&] { check_lvl(c, lvl); r = c->rows(lvl); });
+    return rc == CUHE_OK ? r : -rc;
+}
+
+int cuhe_ctx_set_poly_modulus_host(cuhe_ctx* c, const int64_t* coeffs, int ncoeffs) {
+    return guarded([&] {
+        REQUIRE(c && coeffs, "null argument");
+        const int n = c->par.modLen, N = c->par.nttLen, H = c->par.crtLen;
+        REQUIRE(ncoeffs == n + 1, "polynomial modulus must have modLen+1 coefficients");
+        REQUIRE(coeffs[n] == 1, "polynomial modulus must be monic");
+        DeviceGuard dg(c->device);
+        std::vector<int64_t> phi(coeffs, coeffs + ncoeffs);
+        std::vector<int64_t> u = hm::barrett_u(phi);          // floor(x^(2n-1)/Phi), cuhe/Operations.cu:216-219
+        const int rows = c->rows(0);
+        cudaStream_t st = 0;
+        if (c->d_u_ntt) { cudaFree(c->d_u_ntt); cudaFree(c->d_m_ntt); cudaFree(c->d_m_crt); c->d_u_ntt = nullptr; }
+        CK(cudaMalloc(&c->d_u_ntt, std::max<size_t>(1, (size_t)rows * N * 8)));
+        CK(cudaMalloc(&c->d_m_ntt, std::max<size_t>(1, (size_t)rows * N * 8)));
+        CK(cudaMalloc(&c->d_m_crt, std::max<size_t>(1, (size_t)rows * H * 4)));
+        if (rows > 0) {
+            long long* d_co = nullptr;
+            uint32_t* d_ucrt = nullptr;
+            CK(cudaMalloc(&d_co, (size_t)n * 8));
+            CK(cudaMalloc(&d_ucrt, (size_t)rows * H * 4));
+            dim3 grid((H + 255) / 256, rows);
+            // m' = Phi - x^n  (cuhe/Operations.cu:224)
+            CK(cudaMemcpy(d_co, phi.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
+            small_poly_crt_kernel<<<grid, 256, 0, st>>>(c->d_m_crt, d_co, n, c->pv(), H);
+            CK(cudaGetLastError());
+            fwd_ntt(c, N, c->d_m_ntt, c->d_m_crt, H, rows, nullptr, 1, st);
+            CK(cudaStreamSynchronize(st));
+            CK(cudaMemcpy(d_co, u.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
+            small_poly_crt_kernel<<<grid, 256, 0, st>>>(d_ucrt, d_co, n, c->pv(), H);
+            CK(cudaGetLastError());
+            fwd_ntt(c, N, c->d_u_ntt, d_ucrt, H, rows, nullptr, 1, st);
+            CK(cudaStreamSynchronize(st));
+            cudaFree(d_co); cudaFree(d_ucrt);
+        }
+        c->have_polymod = true;
+    });
+}
+
+int cuhe_malloc(cuhe_ctx* c, void** ptr, size_t bytes, cuhe_stream stream) {
+    return guarded([&] { REQUIRE(c && ptr, "null argument"); DeviceGuard dg(c->device); *ptr = pool_alloc(c, bytes, (cudaStream_t)stream); });
+}
+int cuhe_free(cuhe_ctx* c, void* ptr, cuhe_stream stream) {
+    return guarded([&] { REQUIRE(c, "null context"); DeviceGuard dg(c->device); pool_free(ptr, (cudaStream_t)stream); });
+}
+int cuhe_pool_trim(cuhe_ctx* c) {
+    return guarded([&] { REQUIRE(c, "null context"); DeviceGuard dg(c->device); CK(cudaDeviceSynchronize()); CK(cudaMemPoolTrimTo(c->pool, 0)); });
+}
+
+int cuhe_crt(cuhe_ctx* c, uint32_t* dst, const uint32_t* raw, int lvl, cuhe_stream stream) {
+    return guarded([&] {
+        check_lvl(c, lvl); REQUIRE(dst && raw, "null pointer");
+        DeviceGuard dg(c->device);
+        const int rows = c->rows(lvl), W = c->par.wordsCoeffAt(lvl), H = c->par.crtLen;
+        if (rows == 0) return;
+        const size_t smem = (size_t)kCrtThreads * (W | 1) * 4;
+        crt_kernel<<<(H + kCrtThreads - 1) / kCrtThreads, kCrtThreads, smem, (cudaStream_t)stream>>>(
+            dst, raw, c->pv(), rows, c->d_pow32, c->pow_stride, W, c->par.modLen, H);
+        count_launch();
+        CK(cudaGetLastError());
+    });
+}
+
+int cuhe_icrt(cuhe_ctx* c, uint32_t* raw_out, const uint32_t* crt_all, int lvl, int b, int e, cuhe_stream stream) {
+    return guarded([&] {
+        check_lvl(c, lvl); REQUIRE(raw_out && crt_all, "null pointer");
+        REQUIRE(0 <= b && b <= e && e <= c->par.crtLen, "coefficient range out of bounds");
+        DeviceGuard dg(c->device);
+        if (e > c->par.modLen) e = c->par.modLen;     // the reference writes idx < modLen only
+        if (b >= e) return;
+        const IcrtDev& ic = c->icrt[lvl];
+        cudaStream_t st = (cudaStream_t)stream;
+        if (ic.W <= 8) launch_icrt<8>(raw_out, crt_all, c, ic, b, e, st);
+        else if (ic.W <= 20) launch_icrt<20>(raw_out, crt_all, c, ic, b, e, st);
+        else if (ic.W <= 36) launch_icrt<36>(raw_out, crt_all, c, ic, b, e, st);
+        else if (ic.W <= 52) launch_icrt<52>(raw_out, crt_all, c, ic, b, e, st);
+        else if (ic.W <= 104) launch_icrt<104>(raw_out, crt_all, c, ic, b, e, st);
+        else throw ArgError{"coefficient modulus wider than 104 words"};
+        CK(cudaGetLastError());
+    });
+}
+
+int cuhe_ntt(cuhe_ctx* c, uint64_t* dst, const uint32_t* src, int lvl, cuhe_stream stream) {
+    return guarded([&] {
+        check_lvl(c, lvl); REQUIRE(dst && src, "null pointer");
+        DeviceGuard dg(c->device);
+        fwd_ntt(c, c->par.nttLen, dst, src, c->par.crtLen, c->rows(lvl), nullptr, 1, (cudaStream_t)stream);
+    });
+}
+int cuhe_intt_double_deg(cuhe_ctx* c, uint32_t* dst, const uint64_t* src, int lvl, cuhe_stream stream) {
+    return guarded([&] {
+        check_lvl(c, lvl); REQUIRE(dst && src, "null pointer");
+        DeviceGuard dg(c->device);
+        const int rows = c->rows(lvl);
+        inv_ntt_modp(c, c->par.nttLen, dst, src, nullptr, rows, rows, (cudaStream_t)stream);
+    });
+}
+int cuhe_intt(cuhe_ctx* c, uint32_t* dst, const uint64_t* src, int lvl, cuhe_stream stream) {
+    return guarded([&] {
+        check_lvl(c, lvl); REQUIRE(dst && src, "null pointer");
+        DeviceGuard dg(c->device);
+        const int rows = c->rows(lvl), N = c->par.nttLen, H = c->par.crtLen;
+        if (rows == 0) return;
+        cudaStream_t st = (cudaStream_t)stream;
+        Tmp hold(c, (size_t)rows * N * 4, st);
+        inv_ntt_modp(c, N, hold.as<uint32_t>(), src, nullptr, rows, rows, st);
+        dim3 grid((H + 255) / 256, rows);
+        take_low_half_kernel<<<grid, 256, 0, st>>>(dst, hold.as<uint32_t>(), H, N);
+        count_launch();
+        CK(cudaGetLastError());
+    });
+}
+int cuhe_barrett(cuhe_ctx* c, uint32_t* dst, const uint32_t* hold, int lvl, cuhe_stream stream) {
+    return guarded([&] {
+        check_lvl(c, lvl); REQUIRE(dst && hold, "null pointer");
+        DeviceGuard dg(c->device);
+        barrett_impl(c, dst, hold, lvl, (cudaStream_t)stream);
+    });
+}
+static void intt_mod_impl(cuhe_ctx* c, uint32_t* dst, const uint64_t* x, const uint64_t* y, int lvl, cudaStream_t st) {
+    const int rows = c->rows(lvl), N = c->par.nttLen;
+    if (rows == 0) return;
+    if (!c->have_polymod) throw StateError{"Barrett reduction needs cuhe_ctx_set_poly_modulus_host first"};
+    Tmp hold(c, (size_t)rows * N * 4, st);
+    inv_ntt_modp(c, N, hold.as<uint32_t>(), x, y, rows, rows, st);
+    barrett_impl(c, dst, hold.as<uint32_t>(), lvl, st);
+}
+int cuhe_intt_mod(cuhe_ctx* c, uint32_t* dst, const uint64_t* src, int lvl, cuhe_stream stream) {
+    return guarded([&] {
+        check_lvl(c, lvl); REQUIRE(dst && src, "null pointer");
+        DeviceGuard dg(c->device);
+        intt_mod_impl(c, dst, src, nullptr, lvl, (cudaStream_t)stream);
+    });
+}
+int cuhe_ntt_mul_intt_mod(cuhe_ctx* c, uint32_t* dst, const uint64_t* x, const uint64_t* y, int lvl, cuhe_stream stream) {
+    return guarded([&] {
+        check_lvl(c, lvl); REQUIRE(dst && x && y, "null pointer");
+        DeviceGuard dg(c->device);
+        intt_mod_impl(c, dst, x, y, lvl, (cudaStream_t)stream);
+    });
+}
+
+static int pointwise(cuhe_ctx* c, uint64_t* z, const uint64_t* x, const uint64_t* y, int lvl, cuhe_stream stream,
+                     bool mul, bool nx1) {
+    return guarded([&] {
+        check_lvl(c, lvl); REQUIRE(z && x && y, "null pointer");
+        DeviceGuard dg(c->device);
+        const int rows = c->rows(lvl), N = c->par.nttLen;
+        if (rows == 0) return;
+        dim3 grid(N / 2 / 256, rows);
+        const long long ys = nx1 ? 0 : N;
+        if (mul) ntt_pointwise_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(z, x, y, ys, N);
+        else ntt_pointwise_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(z, x, y, ys, N);
+        count_launch();
+        CK(cudaGetLastError());
+    });
+}
+int cuhe_ntt_mul(cuhe_ctx* c, uint64_t* z, const uint64_t* x, const uint64_t* y, int lvl, cuhe_stream s) { return pointwise(c, z, x, y, lvl, s, true, false); }
+int cuhe_ntt_add(cuhe_ctx* c, uint64_t* z, const uint64_t* x, const uint64_t* y, int lvl, cuhe_stream s) { return pointwise(c, z, x, y, lvl, s, false, false); }
+int cuhe_ntt_mul_nx1(cuhe_ctx* c, uint64_t* z, const uint64_t* x, const uint64_t* y, int lvl, cuhe_stream s) { return pointwise(c, z, x, y, lvl, s, true, true); }
+int cuhe_ntt_add_nx1(cuhe_ctx* c, uint64_t* z, const uint64_t* x, const uint64_t* y, int lvl, cuhe_stream s) { return pointwise(c, z, x, y, lvl, s, false, true); }
+
+static int crt_add_common(cuhe_ctx* c, uint32_t* sum, const uint32_t* x, const uint32_t* y, int lvl, cuhe_stream stream, bool nx1) {
+    return guarded([&] {
+        check_lvl(c, lvl); REQUIRE(sum && x && y, "null pointer");
+        DeviceGuard dg(c->device);
+        const int rows = c->rows(lvl), H = c->par.crtLen, n = c->par.modLen;
+        if (rows == 0) return;
+        dim3 grid((n + 255) / 256, rows);
+        crt_add_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(sum, x, y, nx1 ? 0 : H, c->pv(), n, H);
+        count_launch();
+        CK(cudaGetLastError());
+    });
+}
+int cuhe_crt_add(cuhe_ctx* c, uint32_t* sum, const uint32_t* x, const uint32_t* y, int lvl, cuhe_stream s) { return crt_add_common(c, sum, x, y, lvl, s, false); }
+int cuhe_crt_add_nx1(cuhe_ctx* c, uint32_t* sum, const uint32_t* x, const uint32_t* y, int lvl, cuhe_stream s) { return crt_add_common(c, sum, x, y, lvl, s, true); }
+int cuhe_crt_add_int(cuhe_ctx* c, uint32_t* sum, const uint32_t* x, unsigned a, int lvl, cuhe_stream stream) {
+    return guarded([&] {
+        check_lvl(c, lvl); REQUIRE(sum && x, "null pointer");
+        DeviceGuard dg(c->device);
+        const int rows = c->rows(lvl);
+        if (rows == 0) return;
+        crt_add_int_kernel<<<(rows + 63) / 64, 64, 0, (cudaStream_t)stream>>>(sum, x, a, c->pv(), rows, c->par.crtLen);
+        count_launch();
+        CK(cudaGetLastError());
+    });
+}
+
+int cuhe_mod_switch(cuhe_ctx* c, uint32_t* dst, const uint32_t* src, const uint32_t* last_row, int lvl, cuhe_stream stream) {
+    return guarded([&] {
+        check_lvl(c, lvl); REQUIRE(dst && src && last_row, "null pointer");
+        REQUIRE(lvl + 1 < c->par.depth, "cannot modSwitch on the last level");
+        DeviceGuard dg(c->device);
+        const int rows = c->rows(lvl), n = c->par.modLen;
+        if (rows == 0) return;
+        dim3 grid((n + 127) / 128, rows);
+        modswitch_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(dst, src, last_row, c->pv(), rows, c->L(lvl), c->d_invp, n,
+                                                               c->par.crtLen, c->par.modMsg);
+        count_launch();
+        CK(cudaGetLastError());
+    });
+}
+
+int cuhe_relin_init(cuhe_ctx* c, const uint32_t* evalkeys_raw, cuhe_stream stream) {
+    return guarded([&] {
+        REQUIRE(c && evalkeys_raw, "null argument");
+        REQUIRE(c->par.logRelin > 0 && c->par.numEvalKey > 0, "parameters have no relinearization (w = 0)");
+        DeviceGuard dg(c->device);
+        cudaStream_t st = (cudaStream_t)stream;
+        const int K = c->par.numEvalKey, rows = c->rows(0), N = c->par.nttLen, H = c->par.crtLen, W = c->par.wordsCoeffAt(0);
+        if (c->d_ek) { cudaFree(c->d_ek); c->d_ek = nullptr; }
+        CK(cudaMalloc(&c->d_ek, std::max<size_t>(1, (size_t)rows * K * N * 8)));
+        if (rows == 0) return;
+        Tmp crt(c, (size_t)rows * H * 4, st), ntt(c, (size_t)rows * N * 8, st);
+        const size_t smem = (size_t)kCrtThreads * (W | 1) * 4;
+        for (int k = 0; k < K; k++) {
+            crt_kernel<<<(H + kCrtThreads - 1) / kCrtThreads, kCrtThreads, smem, st>>>(
+                crt.as<uint32_t>(), evalkeys_raw + (size_t)k * H * W, c->pv(), rows, c->d_pow32, c->pow_stride, W,
+                c->par.modLen, H);
+            CK(cudaGetLastError());
+            fwd_ntt(c, N, ntt.as<uint64_t>(), crt.as<uint32_t>(), H, rows, nullptr, 1, st);
+            // ek[r][k][.] <- ntt[r][.]
+            CK(cudaMemcpy2DAsync(c->d_ek + (size_t)k * N, (size_t)K * N * 8, ntt.as<uint64_t>(), (size_t)N * 8, (size_t)N * 8,
+                                 rows, cudaMemcpyDeviceToDevice, st));
+        }
+        CK(cudaStreamSynchronize(st));
+    });
+}
+
+int cuhe_relin(cuhe_ctx* c, uint64_t* dst, const uint32_t* raw, int lvl, cuhe_stream stream) {
+    return guarded([&] {
+        check_lvl(c, lvl); REQUIRE(dst && raw, "null pointer");
+        if (!c->d_ek) throw StateError{"cuhe_relin_init has not been called"};
+        DeviceGuard dg(c->device);
+        cudaStream_t st = (cudaStream_t)stream;
+        const int K = c->par.numEvalKeyAt(lvl), K0 = c->par.numEvalKey, rows = c->rows(lvl), N = c->par.nttLen;
+        if (rows == 0) return;
+        const NttPlan& pl = get_plan(c, N);
+        // digit transforms, prime independent (nttw, cuhe/Operations.cu:399-403)
+        Tmp D(c, (size_t)K * N * 8, st), scratch(c, (size_t)K * N * 8, st);
+        Pass1Args a{};
+        a.scratch = scratch.as<uint64_t>(); a.src = raw; a.tw1 = pl.tw1; a.n2 = pl.n2;
+        a.digit_w = c->par.logRelin; a.digit_words = c->par.wordsCoeffAt(lvl); a.digit_first = 0;
+        CK(launch_pass1(IN_DIGIT, a, K, st));
+        Pass2Args b{};
+        b.dst = D.as<uint64_t>(); b.scratch = scratch.as<uint64_t>(); b.tw2 = pl.tw2; b.dst_stride = N; b.row_mod = 1;
+        CK(launch_pass2(pl.r3, OUT_U64, b, K, st));
+        dim3 grid((N + 255) / 256, rows);
+        relin_mac_kernel<<<grid, 256, 0, st>>>(dst, D.as<uint64_t>(), c->d_ek, K, (long long)N, (long long)K0 * N, 0, 1, N);
+        count_launch();
+        CK(cudaGetLastError());
+    });
+}
+
+int cuhe_ntt_ext_batch(cuhe_ctx* c, uint64_t* dst, const uint32_t* src, int nttLen, int count, long long src_stride,
+                       cuhe_stream stream) {
+    return guarded([&] {
+        REQUIRE(c && dst && src, "null argument"); REQUIRE(count >= 0 && count <= 65535, "batch must be in [0, 65535]");
+        DeviceGuard dg(c->device);
+        fwd_ntt(c, nttLen, dst, src, src_stride, count, nullptr, 1, (cudaStream_t)stream);
+    });
+}
+int cuhe_intt_batch(cuhe_ctx* c, uint64_t* dst, const uint64_t* src, int nttLen, int count, cuhe_stream stream) {
+    return guarded([&] {
+        REQUIRE(c && dst && src, "null argument"); REQUIRE(count >= 0 && count <= 65535, "batch must be in [0, 65535]");
+        DeviceGuard dg(c->device);
+        cudaStream_t st = (cudaStream_t)stream;
+        const NttPlan& pl = get_plan(c, nttLen);
+        Tmp scratch(c, (size_t)count * nttLen * 8, st);
+        Pass1Args a{};
+        a.scratch = scratch.as<uint64_t>(); a.src = src; a.tw1 = pl.tw1s; a.src_stride = nttLen; a.n2 = pl.n2;
+        CK(launch_pass1(IN_U64_REV, a, count, st));
+        Pass2Args b{};
+        b.dst = dst; b.scratch = scratch.as<uint64_t>(); b.tw2 = pl.tw2; b.dst_stride = nttLen; b.row_mod = 1;
+        CK(launch_pass2(pl.r3, OUT_U64, b, count, st));
+    });
+}
+
+int cuhe_modp_batch(cuhe_ctx* c, int op, uint64_t* out, const uint64_t* x, const uint64_t* y, size_t n, int shift,
+                    cuhe_stream stream) {
+    return guarded([&] {
+        REQUIRE(c && out && x, "null argument"); REQUIRE(op >= 0 && op <= 3, "bad op");
+        REQUIRE(op == 3 || y, "null argument"); REQUIRE(shift >= 0 && shift < 192, "shift out of range");
+        DeviceGuard dg(c->device);
+        if (n == 0) return;
+        modp_batch_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(op, out, x, y, n, shift);
+        count_launch();
+        CK(cudaGetLastError());
+    });
+}
+
+int cuhe_mul_raw_host(cuhe_ctx* c, uint32_t* out_h, const uint32_t* a_h, const uint32_t* b_h, int lvl, cuhe_stream stream) {
+    return guarded([&] {
+        check_lvl(c, lvl); REQUIRE(out_h && a_h && b_h, "null pointer");
+        REQUIRE(c->world == 1, "cuhe_mul_raw_host needs an unsharded context");
+        DeviceGuard dg(c->device);
+        cudaStream_t st = (cudaStream_t)stream;
+        const int L = c->L(lvl), W = c->par.wordsCoeffAt(lvl), H = c->par.crtLen, N = c->par.nttLen;
+        const size_t raw_b = (size_t)H * W * 4;
+        Tmp ra(c, raw_b, st), rb(c, raw_b, st), ca(c, (size_t)L * H * 4, st), cb(c, (size_t)L * H * 4, st);
+        Tmp na(c, (size_t)L * N * 8, st), nb(c, (size_t)L * N * 8, st);
+        CK(cudaMemcpyAsync(ra.p, a_h, raw_b, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(rb.p, b_h, raw_b, cudaMemcpyHostToDevice, st));
+        const size_t smem = (size_t)kCrtThreads * (W | 1) * 4;
+        const int cg = (H + kCrtThreads - 1) / kCrtThreads;
+        crt_kernel<<<cg, kCrtThreads, smem, st>>>(ca.as<uint32_t>(), ra.as<uint32_t>(), c->pv(), L, c->d_pow32, c->pow_stride, W, c->par.modLen, H);
+        count_launch();
+        crt_kernel<<<cg, kCrtThreads, smem, st>>>(cb.as<uint32_t>(), rb.as<uint32_t>(), c->pv(), L, c->d_pow32, c->pow_stride, W, c->par.modLen, H);
+        count_launch();
+        CK(cudaGetLastError());
+        fwd_ntt(c, N, na.as<uint64_t>(), ca.as<uint32_t>(), H, L, nullptr, 1, st);
+        fwd_ntt(c, N, nb.as<uint64_t>(), cb.as<uint32_t>(), H, L, nullptr, 1, st);
+        intt_mod_impl(c, ca.as<uint32_t>(), na.as<uint64_t>(), nb.as<uint64_t>(), lvl, st);
+        // c2r + r2z (cuhe/CuHE.cu:366-382, 333-348)
+        CK(cudaMemsetAsync(ra.p, 0, raw_b, st));
+        const IcrtDev& ic = c->icrt[lvl];
+        const int e = c->par.modLen;
+        if (ic.W <= 8) launch_icrt<8>(ra.as<uint32_t>(), ca.as<uint32_t>(), c, ic, 0, e, st);
+        else if (ic.W <= 20) launch_icrt<20>(ra.as<uint32_t>(), ca.as<uint32_t>(), c, ic, 0, e, st);
+        else if (ic.W <= 36) launch_icrt<36>(ra.as<uint32_t>(), ca.as<uint32_t>(), c, ic, 0, e, st);
+        else if (ic.W <= 52) launch_icrt<52>(ra.as<uint32_t>(), ca.as<uint32_t>(), c, ic, 0, e, st);
+        else launch_icrt<104>(ra.as<uint32_t>(), ca.as<uint32_t>(), c, ic, 0, e, st);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(out_h, ra.p, raw_b, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    });
+}
+
+}  // extern "C"

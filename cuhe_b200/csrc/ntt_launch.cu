@@ -1,0 +1,65 @@
+// cuhe_b200/csrc/ntt_launch.cu -- instantiation + launch of the NTT pass kernels.
+#include <cuda_runtime.h>
+#include "engine.hpp"
+#include "ntt.cuh"
+
+namespace cuhe_b200 {
+
+template <int MODE>
+static cudaError_t launch_p1(const Pass1Args& a, int count, cudaStream_t st) {
+    dim3 grid(a.n2 / 128, count);
+    ntt_pass1_kernel<MODE><<<grid, 128, 0, st>>>(a);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pass1(int mode, const Pass1Args& a, int count, cudaStream_t st) {
+    if (count <= 0) return cudaSuccess;
+    switch (mode) {
+        case IN_EXT_U32: return launch_p1<IN_EXT_U32>(a, count, st);
+        case IN_DIGIT: return launch_p1<IN_DIGIT>(a, count, st);
+        case IN_U64_REV: return launch_p1<IN_U64_REV>(a, count, st);
+        case IN_U64_REV_MUL: return launch_p1<IN_U64_REV_MUL>(a, count, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <int R3, int OUT>
+static cudaError_t launch_p2(const Pass2Args& a, int count, cudaStream_t st) {
+    using Cfg = Pass2Cfg<R3>;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(ntt_pass2_kernel<R3, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Cfg::SMEM);
+        if (e != cudaSuccess) return e;
+        attr_set[dev] = true;
+    }
+    dim3 grid(64 / Cfg::R, count);
+    ntt_pass2_kernel<R3, OUT><<<grid, 128, Cfg::SMEM, st>>>(a);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <int R3>
+static cudaError_t launch_p2_out(int out, const Pass2Args& a, int count, cudaStream_t st) {
+    switch (out) {
+        case OUT_U64: return launch_p2<R3, OUT_U64>(a, count, st);
+        case OUT_U64_MUL: return launch_p2<R3, OUT_U64_MUL>(a, count, st);
+        case OUT_U32_MODP: return launch_p2<R3, OUT_U32_MODP>(a, count, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_pass2(int r3, int out, const Pass2Args& a, int count, cudaStream_t st) {
+    if (count <= 0) return cudaSuccess;
+    switch (r3) {
+        case 4: return launch_p2_out<4>(out, a, count, st);
+        case 8: return launch_p2_out<8>(out, a, count, st);
+        case 16: return launch_p2_out<16>(out, a, count, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace cuhe_b200

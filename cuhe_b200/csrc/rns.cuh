@@ -1,0 +1,260 @@
+// cuhe_b200/csrc/rns.cuh
+// Residue-number-system kernels around the NTT: CRT, ICRT, modulus switching,
+// pointwise NTT-domain and CRT-domain arithmetic, the tail of the polynomial
+// Barrett reduction and the relinearization inner product.
+//
+// Replaces cuhe/Base.cu:845-1138.  Differences from the reference, by design:
+//   * one launch covers all residues (grid over {coefficient x residue}); the
+//     reference walks residues serially inside each thread of an N/64-block grid
+//   * tables live in global memory (L2-resident), not __constant__/texture, so
+//     the 103-prime limit of cuhe/Base.cu:139 is gone
+//   * residues may be a strided subset of the prime list (prime index =
+//     base + step*row) so the same kernels serve a residue-sharded multi-GPU run
+#pragma once
+#include <cstdint>
+#include "engine.hpp"
+#include "modp.cuh"
+
+namespace cuhe_b200 {
+
+__device__ __forceinline__ int prime_index(const PrimeView& v, int row) { return v.base + v.step * row; }
+
+// ---------------------------------------------------------------------------
+// CRT: raw u32[H][W] -> u32[rows][H].                       (cuhe/Base.cu:857-879)
+// residue = sum_k word_k * (2^(32k) mod p)  mod p, one 64-bit accumulator per
+// (coefficient, prime); pow32[l][k] = 2^(32k) mod p_l.  Only idx < n is written.
+// ---------------------------------------------------------------------------
+constexpr int kCrtThreads = 128;
+__global__ void __launch_bounds__(kCrtThreads)
+crt_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ raw, PrimeView pv, int rows,
+           const uint32_t* __restrict__ pow32, int pow_stride, int W, int n, int H) {
+    extern __shared__ uint32_t sw[];      // [kCrtThreads][W | 1]
+    const int ws = W | 1;                 // odd stride: conflict-free column reads
+    const int i0 = blockIdx.x * kCrtThreads;
+    const int cnt = min(kCrtThreads, H - i0);
+    for (int e = threadIdx.x; e < cnt * W; e += kCrtThreads) {
+        int c = e / W, k = e - c * W;
+        sw[c * ws + k] = raw[(long long)i0 * W + e];
+    }
+    __syncthreads();
+    const int i = i0 + threadIdx.x;
+    if (i >= n) {
+        if (i < H) for (int r = 0; r < rows; r++) dst[(long long)r * H + i] = 0;
+        return;
+    }
+    const uint32_t* c = sw + threadIdx.x * ws;
+    for (int r = 0; r < rows; r++) {
+        const int l = prime_index(pv, r);
+        const uint32_t* pw = pow32 + (long long)l * pow_stride;
+        uint64_t acc = 0;                 // p < 2^26 (checked at init): 16 terms < 2^62
+        uint64_t acc_hi = 0;
+        for (int k = 0; k < W; k++) {
+            acc += (uint64_t)c[k] * __ldg(pw + k);
+            if ((k & 15) == 15) { acc_hi += acc >> 32; acc &= 0xFFFFFFFFull; }
+        }
+        // value = acc + acc_hi*2^32 ; fold with 2^32 mod p = pw[1]
+        const uint32_t p = pv.p[l];
+        const uint64_t mu = pv.mu[l];
+        uint64_t t = mod_u64_u32(acc_hi, p, mu);
+        uint64_t v = t * (W > 1 ? __ldg(pw + 1) : (uint32_t)((1ull << 32) % p)) + mod_u64_u32(acc, p, mu);
+        dst[(long long)r * H + i] = mod_u64_u32(v, p, mu);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// ICRT: u32[L][H] -> raw u32[H][W]                          (cuhe/Base.cu:845-924)
+// coeff = sum_l ((c_l * b_l mod p_l) * M_l), one conditional subtraction of M
+// after every term (same accumulate / compare / subtract order as the
+// reference, M_l byte-truncated to Wp words exactly as loaded there).
+// Takes ALL L residues of the level (after an all-gather when sharded).
+// ---------------------------------------------------------------------------
+template <int WMAX>
+__global__ void __launch_bounds__(128)
+icrt_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, const uint32_t* __restrict__ primes,
+            const uint64_t* __restrict__ mus, const uint32_t* __restrict__ M, const uint32_t* __restrict__ mi,
+            const uint32_t* __restrict__ bi, int L, int W, int Wp, int i_begin, int i_end, int H) {
+    const int idx = i_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= i_end) return;
+    uint32_t sum[WMAX + 1];
+#pragma unroll
+    for (int k = 0; k <= WMAX; k++) sum[k] = 0;
+    for (int l = 0; l < L; l++) {
+        const uint32_t p = primes[l];
+        const uint64_t mu = mus[l];
+        uint64_t tar = mod_u64_u32(src[(long long)l * H + idx], p, mu);
+        const uint32_t tt = mod_u64_u32(tar * bi[l], p, mu);
+        const uint32_t* m = mi + (long long)l * Wp;
+        uint64_t carry = 0;
+#pragma unroll
+        for (int k = 0; k <= WMAX; k++) {
+            if (k <= W) {
+                uint64_t t = (uint64_t)sum[k] + carry;
+                if (k < Wp) t += (uint64_t)tt * __ldg(m + k);
+                sum[k] = (uint32_t)t;
+                carry = t >> 32;
+            }
+        }
+        // sum >= M ?  (leq_M, cuhe/Base.cu:846-856)
+        bool ge = true;
+        bool decided = false;
+#pragma unroll
+        for (int k = WMAX; k >= 0; k--) {
+            if (k <= W && !decided) {
+                const uint32_t mk = (k < W) ? __ldg(M + k) : 0u;
+                if (sum[k] != mk) { ge = sum[k] > mk; decided = true; }
+            }
+        }
+        if (ge) {
+            uint32_t borrow = 0;
+#pragma unroll
+            for (int k = 0; k <= WMAX; k++) {
+                if (k <= W) {
+                    const uint32_t mk = (k < W) ? __ldg(M + k) : 0u;
+                    uint64_t t = (uint64_t)sum[k] - mk - borrow;
+                    sum[k] = (uint32_t)t;
+                    borrow = (uint32_t)(t >> 63);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < WMAX; k++)
+        if (k < W) dst[(long long)idx * W + k] = sum[k];
+}
+
+// ---------------------------------------------------------------------------
+// modulus switching                                        (cuhe/Base.cu:1112-1138)
+// d = c_last (+- ep*p_last to clear the message parity, signed 32-bit exactly
+// as the reference's `int dirty`), then c_j <- (c_j - d) * p_last^-1 mod p_j.
+// `last` is the dropped residue row (local or received from its owner rank).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+modswitch_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, const uint32_t* __restrict__ last,
+                 PrimeView pv, int rows, int Llevel, const uint32_t* __restrict__ invp, int n, int H, int modmsg) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (idx >= n || r >= rows) return;
+    const int j = prime_index(pv, r);
+    if (j >= Llevel - 1) return;
+    int dirty = (int)last[idx];
+    const uint32_t pt = pv.p[Llevel - 1];
+    const int ep = dirty % modmsg;
+    if (ep != 0) {
+        if ((uint32_t)dirty > ((pt - 1) / 2)) dirty = (int)((uint32_t)dirty - (uint32_t)ep * pt);
+        else dirty = (int)((uint32_t)dirty + (uint32_t)ep * pt);
+    }
+    const uint32_t p = pv.p[j];
+    const uint64_t mu = pv.mu[j];
+    // (c - d) mod p, computed on a non-negative 64-bit offset
+    long long v = (long long)src[(long long)r * H + idx] - (long long)dirty;
+    uint64_t u = (uint64_t)(v + ((long long)p << 32));          // p*2^32 == 0 mod p, > |v|
+    uint64_t tt = (uint64_t)mod_u64_u32(u, p, mu) * invp[(Llevel - 1) * (Llevel - 2) / 2 + j];
+    dst[(long long)r * H + idx] = mod_u64_u32(tt, p, mu);
+}
+
+// ---------------------------------------------------------------------------
+// pointwise NTT-domain ops                                (cuhe/Base.cu:1036-1075)
+// y_stride == 0 gives the _nx1 broadcast variants.
+// ---------------------------------------------------------------------------
+template <bool MUL>
+__global__ void __launch_bounds__(256)
+ntt_pointwise_kernel(uint64_t* __restrict__ z, const uint64_t* __restrict__ x, const uint64_t* __restrict__ y,
+                     long long y_stride, int N) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    const long long row = blockIdx.y;
+    if (i >= N) return;
+    const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(x + row * N + i);
+    const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(y + row * y_stride + i);
+    ulonglong2 c;
+    if constexpr (MUL) { c.x = mul_modP(a.x, b.x); c.y = mul_modP(a.y, b.y); }
+    else { c.x = add_modP(a.x, b.x); c.y = add_modP(a.y, b.y); }
+    *reinterpret_cast<ulonglong2*>(z + row * N + i) = c;
+}
+
+// ---------------------------------------------------------------------------
+// CRT-domain adds                                          (cuhe/Base.cu:1088-1109)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+crt_add_kernel(uint32_t* __restrict__ x, const uint32_t* __restrict__ a, const uint32_t* __restrict__ b,
+               long long b_stride, PrimeView pv, int n, int H) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (i >= n) return;
+    const int l = prime_index(pv, r);
+    uint64_t s = (uint64_t)a[(long long)r * H + i] + b[(long long)r * b_stride + i];
+    x[(long long)r * H + i] = mod_u64_u32(s, pv.p[l], pv.mu[l]);
+}
+__global__ void crt_add_int_kernel(uint32_t* __restrict__ y, const uint32_t* __restrict__ x, unsigned a,
+                                   PrimeView pv, int rows, int H) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const int l = prime_index(pv, r);
+    const uint32_t p = pv.p[l];
+    y[(long long)r * H] = (uint32_t)(((uint64_t)x[(long long)r * H] + (a % p)) % p);
+}
+
+// ---------------------------------------------------------------------------
+// tail of the polynomial Barrett reduction: barrett_sub_1 / sub_2 / sub_mc and
+// the copy-out (cuhe/Base.cu:951-1001, cuhe/Operations.cu:485-500) in one pass.
+//   f = hold[r][.] (INTT of the product), t = u*(f>>(n-1)), s = m'*q
+//   out[i] = f[i] - (i>=n ? t[i] : 0) - s[i]  (mod p), i < H
+//   and, as the reference does, if that value at i == n is non-zero subtract
+//   m' once more from coefficients 0..n-2.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+barrett_finish_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ hold, const uint32_t* __restrict__ t,
+                      const uint32_t* __restrict__ s, const uint32_t* __restrict__ m_crt, PrimeView pv,
+                      int n, int H, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (i >= H) return;
+    const int l = prime_index(pv, r);
+    const uint32_t p = pv.p[l];
+    const long long base = (long long)r * N;
+    auto subp = [p](uint32_t a, uint32_t b) { if (a < b) a += p; return a - b; };
+    auto val = [&](int k) {
+        uint32_t a = hold[base + k];
+        if (k >= n && k < 2 * n) a = subp(a, t[base + k]);
+        return subp(a, s[base + k]);
+    };
+    uint32_t v = val(i);
+    if (i < n - 1) {
+        const uint32_t flag = val(n);
+        if (flag > 0) v = subp(v, m_crt[(long long)r * H + i]);
+    }
+    out[(long long)r * H + i] = v;
+}
+
+// ---------------------------------------------------------------------------
+// relinearization inner product                           (cuhe/Base.cu:1024-1033)
+// dst[r][i] = sum_k D[k][i] * EK[l(r)][k][i] mod P.  Products are accumulated
+// unreduced in 192 bits and folded once (2^128 == -2^32 mod P).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+relin_mac_kernel(uint64_t* __restrict__ dst, const uint64_t* __restrict__ D, const uint64_t* __restrict__ ek,
+                 int K, long long ek_key_stride, long long ek_prime_stride, int prime_base, int prime_step, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (i >= N) return;
+    const uint64_t* e = ek + (long long)(prime_base + prime_step * r) * ek_prime_stride + i;
+    const uint64_t* d = D + i;
+    uint64_t a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll 4
+    for (int k = 0; k < K; k++) {
+        const uint64_t x = __ldg(d + (long long)k * N);
+        const uint64_t y = __ldcs(e + (long long)k * ek_key_stride);
+        const uint64_t lo = x * y, hi = __umul64hi(x, y);
+        a0 += lo;
+        const uint64_t c0 = a0 < lo;
+        a1 += hi;
+        const uint64_t c1 = a1 < hi;
+        a1 += c0;
+        a2 += c1 + (a1 < c0);
+    }
+    // total = a0 + a1*2^64 + a2*2^128,  2^128 == -2^32 (mod P), a2 < 2^32
+    uint64_t v = reduce128(a1, a0);
+    uint64_t w = shl_modP<32>(a2);
+    dst[(long long)r * N + i] = sub_modP(v, w);
+}
+
+}  // namespace cuhe_b200

@@ -1,0 +1,76 @@
+"""C-ABI surface checks that need no GPU: the library loads, exports every
+symbol include/cuhe_b200.h declares, and its host-only entry points (parameter
+derivation, cuhe/Parameters.cu:53-145) agree with the oracle."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from conftest import C2, PRINCE, ROOT, SIMPLE_DHS, SMALL_RELIN, MID32K, MID64K
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "cuhe_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(cuhe_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_header_symbols_exported(lib):
+    names = _declared_symbols()
+    assert len(names) >= 35
+    for n in names:
+        assert hasattr(lib, n), f"libcuhe_b200.so does not export {n}"
+
+
+def test_binding_table_matches_header(lib):
+    from cuhe_b200._lib import SYMBOLS
+    assert sorted(SYMBOLS) == _declared_symbols()
+
+
+@pytest.mark.parametrize("ps", [SIMPLE_DHS, SMALL_RELIN, PRINCE, MID32K, C2, MID64K, (44, 2, 16, 24, 24, 32767),
+                                (64, 2, 16, 24, 24, 32767)])
+def test_set_parameters_matches_oracle(lib, ps):
+    from cuhe_b200._lib import cuhe_params
+    from oracle import pyoracle as po
+    cp = cuhe_params()
+    assert lib.cuhe_set_parameters(C.byref(cp), *ps) == 0
+    op = po.set_param(*ps)
+    for name, _ in cuhe_params._fields_:
+        assert getattr(cp, name) == getattr(op, name), name
+    for lvl in range(op.depth):
+        assert lib.cuhe_param_num_crt_prime(C.byref(cp), lvl) == op._numCrtPrime(lvl)
+        assert lib.cuhe_param_log_coeff(C.byref(cp), lvl) == op._logCoeff(lvl)
+        assert lib.cuhe_param_words_coeff(C.byref(cp), lvl) == op._wordsCoeff(lvl)
+        if op.logRelin:
+            assert lib.cuhe_param_num_eval_key(C.byref(cp), lvl) == op._numEvalKey(lvl)
+        assert lib.cuhe_param_get_level(C.byref(cp), op._logCoeff(lvl)) == lvl
+    assert lib.cuhe_param_get_level(C.byref(cp), 1) == -1
+
+
+def test_bad_parameters_fail_loudly(lib):
+    from cuhe_b200._lib import cuhe_params
+    cp = cuhe_params()
+    # nttLen would be 2^17: beyond the reference's preload_ntt (cuhe/Base.cu:58-62)
+    assert lib.cuhe_set_parameters(C.byref(cp), 3, 2, 16, 30, 20, 65537) != 0
+    assert b"nttLen" in lib.cuhe_last_error()
+    assert lib.cuhe_param_num_crt_prime(None, 0) < 0
+
+
+def test_python_mirror_raises_without_init(lib):
+    import cuhe_b200 as ch
+    ch.resetParameters()
+    with pytest.raises(ch.CuHEError):
+        ch.initCuHE([1, 1])
+    with pytest.raises(ch.CuHEError):
+        ch.ctx(0)
+
+
+def test_no_oracle_in_product():
+    """The shipped package must not import or reference oracle/."""
+    pkg = os.path.join(ROOT, "cuhe_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "coracle" not in src, f

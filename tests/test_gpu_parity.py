@@ -1,0 +1,428 @@
+"""GPU parity tests: every C-ABI entry point of the hot path against the CPU
+oracle on the same seeded inputs, bit-exact (integer arithmetic; no tolerance).
+They mirror the semantics of the reference's own tests:
+tests/test_ModP.cu (primitives), tests/test_ntt.cu (ext-NTT == DFT) and the
+domain machine exercised by examples/DHS/simple_DHS.cu."""
+import ctypes as C
+import random
+
+import numpy as np
+import pytest
+
+from conftest import C2, MID32K, MID64K, SIMPLE_DHS, SMALL_RELIN, get_oracle
+
+pytestmark = pytest.mark.gpu
+
+P = 0xFFFFFFFF00000001
+
+
+def _torch():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+class Eng:
+    """Thin harness over the raw C ABI for one parameter set."""
+
+    def __init__(self, lib, ps, rank=0, world=1, device=0, with_polymod=True):
+        from cuhe_b200._lib import check, cuhe_params
+        self.lib, self.check = lib, check
+        self.torch = _torch()
+        self.par = cuhe_params()
+        check(lib.cuhe_set_parameters(C.byref(self.par), *ps))
+        self.h = C.c_void_p()
+        check(lib.cuhe_ctx_create(C.byref(self.h), C.byref(self.par), device, rank, world))
+        self.orc = get_oracle(ps)
+        self.dev = f"cuda:{device}"
+        if with_polymod:
+            phi = np.array(self.orc.phi, dtype=np.int64)
+            check(lib.cuhe_ctx_set_poly_modulus_host(self.h, phi.ctypes.data_as(C.c_void_p), len(phi)))
+
+    def close(self):
+        self.lib.cuhe_ctx_destroy(self.h)
+
+    def st(self):
+        return C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+
+    def up(self, a: np.ndarray):
+        a = np.ascontiguousarray(a)
+        view = a.view(np.int32) if a.dtype == np.uint32 else a.view(np.int64)
+        return self.torch.from_numpy(view).to(self.dev)
+
+    def empty(self, shape, dt):
+        t = self.torch
+        return t.zeros(shape, dtype=t.int32 if dt == np.uint32 else t.int64, device=self.dev)
+
+    @staticmethod
+    def dn(t, dt):
+        return t.cpu().numpy().view(dt)
+
+    def rows(self, lvl):
+        return self.lib.cuhe_ctx_rows(self.h, lvl)
+
+    def call(self, name, *args):
+        self.check(getattr(self.lib, name)(self.h, *args))
+
+
+def p(t):
+    return C.c_void_p(t.data_ptr())
+
+
+@pytest.fixture(scope="module")
+def eng16(lib):
+    e = Eng(lib, SIMPLE_DHS)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def eng64(lib):
+    e = Eng(lib, MID64K)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def eng32(lib):
+    e = Eng(lib, MID32K)
+    yield e
+    e.close()
+
+
+def rand_poly_raw(orc, lvl, seed):
+    rng = random.Random(seed)
+    q = orc.moduli[lvl]
+    coeffs = [rng.randrange(q) for _ in range(orc.n)]
+    return coeffs, orc.to_raw(coeffs, lvl)
+
+
+# ---------------------------------------------------------------------------
+# tests/test_ModP.cu semantics: device primitives == big-int arithmetic mod P
+# ---------------------------------------------------------------------------
+def _modp_inputs(n, seed):
+    rng = np.random.default_rng(seed)
+    edge = np.array([0, 1, 2, P - 1, P - 2, 0xFFFFFFFF, 0x100000000, 0xFFFFFFFF00000000, 0x7FFFFFFFFFFFFFFF,
+                     0x8000000000000000, 0xFFFFFFFE00000002, 0xFFFFFFFF], dtype=np.uint64)
+    # rand_array (32/64-bit operands, tests/test_ModP.cu:38-49), reduced to canonical
+    a = rng.integers(0, P, size=n, dtype=np.uint64)
+    b = rng.integers(0, P, size=n, dtype=np.uint64)
+    b[: n // 4] &= np.uint64(0xFFFFFFFF)
+    a[n // 4: n // 2] &= np.uint64(0xFFFFFFFF)
+    ea = np.repeat(edge, len(edge))
+    eb = np.tile(edge, len(edge))
+    return np.concatenate([ea, a]), np.concatenate([eb, b])
+
+
+@pytest.mark.parametrize("op", [0, 1, 2])
+def test_modp_add_sub_mul(eng16, op):
+    x, y = _modp_inputs(1 << 20, 20260924 + op)
+    dx, dy = eng16.up(x), eng16.up(y)
+    out = eng16.empty(x.shape, np.uint64)
+    eng16.call("cuhe_modp_batch", op, p(out), p(dx), p(dy), C.c_size_t(x.size), 0, eng16.st())
+    got = Eng.dn(out, np.uint64)
+    xo, yo = x.astype(object), y.astype(object)
+    want = ((xo + yo) % P, (xo - yo) % P, (xo * yo) % P)[op]
+    assert np.array_equal(got.astype(object), want)
+
+
+def test_modp_shifts(eng16):
+    x, _ = _modp_inputs(1 << 12, 5)
+    dx = eng16.up(x)
+    out = eng16.empty(x.shape, np.uint64)
+    xo = x.astype(object)
+    # the reference only uses l = 3*a*b (tests/test_ModP.cu:57-78); check every l in [0,192)
+    for l in range(192):
+        eng16.call("cuhe_modp_batch", 3, p(out), p(dx), None, C.c_size_t(x.size), l, eng16.st())
+        got = Eng.dn(out, np.uint64)
+        assert np.array_equal(got.astype(object), (xo << l) % P), f"shift {l}"
+
+
+# ---------------------------------------------------------------------------
+# tests/test_ntt.cu semantics: forward ext-NTT for N = 16k/32k/64k on rand() inputs
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("N", [16384, 32768, 65536])
+def test_ntt_ext_batch_vs_oracle(eng16, N):
+    from oracle import oracle as orc
+    from oracle import pyoracle as po
+    rng = np.random.default_rng(N)
+    cnt = 7
+    # test_ntt.cu:115-118: x = rand() (31-bit), stride nttLen between polynomials
+    x = rng.integers(0, 1 << 31, size=(cnt, N), dtype=np.uint32)
+    x[3, : N // 2] = 0xFFFFFFFF          # edge: maximal words
+    x[4, : N // 2] = 0
+    dx = eng16.up(x)
+    out = eng16.empty((cnt, N), np.uint64)
+    eng16.call("cuhe_ntt_ext_batch", p(out), p(dx), N, cnt, C.c_longlong(N), eng16.st())
+    got = Eng.dn(out, np.uint64)
+    want = orc.ntt_ext(x, N)
+    assert np.array_equal(got, want)
+    # and against the O(N^2) definition itself on a few outputs (test_ntt.cu:38-64)
+    idx = [0, 1, 2, 63, 64, 65, 4095, 4096, N // 2, N - 1]
+    assert [int(got[5, i]) for i in idx] == po.ntt_ext_def(x[5], N, idx)
+    # inverse round trip
+    back = eng16.empty((cnt, N), np.uint64)
+    eng16.call("cuhe_intt_batch", p(back), p(out), N, cnt, eng16.st())
+    b = Eng.dn(back, np.uint64)
+    assert np.array_equal(b[:, : N // 2], x[:, : N // 2].astype(np.uint64))
+    assert not b[:, N // 2:].any()
+
+
+def test_ntt_batch_empty_and_large(eng16):
+    N = 16384
+    x = eng16.up(np.zeros((1, N), dtype=np.uint32))
+    out = eng16.empty((1, N), np.uint64)
+    eng16.call("cuhe_ntt_ext_batch", p(out), p(x), N, 0, C.c_longlong(N), eng16.st())   # empty batch is a no-op
+    assert eng16.lib.cuhe_ntt_ext_batch(eng16.h, p(out), p(x), 12345, 1, C.c_longlong(N), eng16.st()) != 0
+
+
+# ---------------------------------------------------------------------------
+# domain conversions and arithmetic, three ring sizes
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("which", ["eng16", "eng32", "eng64"])
+def test_crt_ntt_intt_icrt(which, request):
+    e = request.getfixturevalue(which)
+    o = e.orc
+    for lvl in (0, 1):
+        L, W, H, N = o.L(lvl), o.W(lvl), o.H, o.N
+        coeffs, raw = rand_poly_raw(o, lvl, 100 + lvl)
+        d_raw = e.up(raw)
+        d_crt = e.empty((L, H), np.uint32)
+        e.call("cuhe_crt", p(d_crt), p(d_raw), lvl, e.st())
+        want_crt = o.crt(raw, lvl)
+        assert np.array_equal(Eng.dn(d_crt, np.uint32), want_crt)
+        d_ntt = e.empty((L, N), np.uint64)
+        e.call("cuhe_ntt", p(d_ntt), p(d_crt), lvl, e.st())
+        want_ntt = o.ntt(want_crt)
+        assert np.array_equal(Eng.dn(d_ntt, np.uint64), want_ntt)
+        d_back = e.empty((L, H), np.uint32)
+        e.call("cuhe_intt", p(d_back), p(d_ntt), lvl, e.st())
+        assert np.array_equal(Eng.dn(d_back, np.uint32), want_crt)
+        d_full = e.empty((L, N), np.uint32)
+        e.call("cuhe_intt_double_deg", p(d_full), p(d_ntt), lvl, e.st())
+        assert np.array_equal(Eng.dn(d_full, np.uint32), o.intt_hold(want_ntt))
+        d_raw2 = e.empty((H, W), np.uint32)
+        e.call("cuhe_icrt", p(d_raw2), p(d_crt), lvl, 0, H, e.st())
+        got_raw = Eng.dn(d_raw2, np.uint32)
+        assert np.array_equal(got_raw, o.icrt(want_crt, lvl))
+        assert o.from_raw(got_raw) == coeffs
+
+
+@pytest.mark.parametrize("which", ["eng16", "eng32", "eng64"])
+def test_mul_barrett(which, request):
+    """ctxt x ctxt: NTT-domain product -> inttMod (INTT + polynomial Barrett)."""
+    e = request.getfixturevalue(which)
+    o = e.orc
+    lvl = 0
+    L, H, N = o.L(lvl), o.H, o.N
+    a, ra = rand_poly_raw(o, lvl, 1)
+    b, rb = rand_poly_raw(o, lvl, 2)
+    ca, cb = o.crt(ra, lvl), o.crt(rb, lvl)
+    na, nb = o.ntt(ca), o.ntt(cb)
+    want = o.mul_raw_to_crt(ra, rb, lvl)
+    d_na, d_nb = e.up(na), e.up(nb)
+    d_prod = e.empty((L, N), np.uint64)
+    e.call("cuhe_ntt_mul", p(d_prod), p(d_na), p(d_nb), lvl, e.st())
+    assert np.array_equal(Eng.dn(d_prod, np.uint64), __import__("oracle.oracle", fromlist=["x"]).ntt_mul(na, nb))
+    d_out = e.empty((L, H), np.uint32)
+    e.call("cuhe_intt_mod", p(d_out), p(d_prod), lvl, e.st())
+    assert np.array_equal(Eng.dn(d_out, np.uint32), want)
+    # fused cAnd + n2c
+    d_out2 = e.empty((L, H), np.uint32)
+    e.call("cuhe_ntt_mul_intt_mod", p(d_out2), p(d_na), p(d_nb), lvl, e.st())
+    assert np.array_equal(Eng.dn(d_out2, np.uint32), want)
+    # stand-alone barrett() on the oracle's hold buffer
+    hold = o.intt_hold(Eng.dn(d_prod, np.uint64))
+    d_out3 = e.empty((L, H), np.uint32)
+    e.call("cuhe_barrett", p(d_out3), p(e.up(hold)), lvl, e.st())
+    assert np.array_equal(Eng.dn(d_out3, np.uint32), want)
+    if which == "eng16":
+        # independent pin: exact big-int (a*b mod Phi) mod q (NTL host path, DHS.cu:219-221)
+        ex = o.mul_exact(a, b, lvl)
+        got = Eng.dn(d_out, np.uint32)
+        for l in range(L):
+            assert np.array_equal(got[l, :o.n], np.array([v % o.primes[l] for v in ex], dtype=np.uint32))
+
+
+def test_pointwise_and_crt_adds(eng16):
+    e, o = eng16, eng16.orc
+    from oracle import oracle as orc
+    lvl = 1
+    L, H, N = o.L(lvl), o.H, o.N
+    rng = np.random.default_rng(9)
+    x = rng.integers(0, P, size=(L, N), dtype=np.uint64)
+    y = rng.integers(0, P, size=(L, N), dtype=np.uint64)
+    dx, dy = e.up(x), e.up(y)
+    dz = e.empty((L, N), np.uint64)
+    e.call("cuhe_ntt_add", p(dz), p(dx), p(dy), lvl, e.st())
+    assert np.array_equal(Eng.dn(dz, np.uint64), orc.ntt_add(x, y))
+    e.call("cuhe_ntt_mul_nx1", p(dz), p(dx), p(dy), lvl, e.st())
+    assert np.array_equal(Eng.dn(dz, np.uint64), orc.ntt_mul(x, np.broadcast_to(y[0], x.shape).copy()))
+    e.call("cuhe_ntt_add_nx1", p(dz), p(dx), p(dy), lvl, e.st())
+    assert np.array_equal(Eng.dn(dz, np.uint64), orc.ntt_add(x, np.broadcast_to(y[0], x.shape).copy()))
+    pr = np.array(o.primes[:L], dtype=np.uint64)[:, None]
+    a = (rng.integers(0, 1 << 40, size=(L, H), dtype=np.uint64) % pr).astype(np.uint32)
+    b = (rng.integers(0, 1 << 40, size=(L, H), dtype=np.uint64) % pr).astype(np.uint32)
+    a[:, o.n:] = 0
+    b[:, o.n:] = 0
+    da, db = e.up(a), e.up(b)
+    ds = e.empty((L, H), np.uint32)
+    e.call("cuhe_crt_add", p(ds), p(da), p(db), lvl, e.st())
+    assert np.array_equal(Eng.dn(ds, np.uint32), o.crt_add(a, b))
+    sc = (rng.integers(0, 2, size=H, dtype=np.uint32))
+    e.call("cuhe_crt_add_nx1", p(ds), p(da), p(e.up(sc)), lvl, e.st())
+    assert np.array_equal(Eng.dn(ds, np.uint32), o.crt_add_nx1(a, sc))
+    ds2 = e.up(a)
+    e.call("cuhe_crt_add_int", p(ds2), p(da), C.c_uint(1), lvl, e.st())
+    assert np.array_equal(Eng.dn(ds2, np.uint32), o.crt_add_int(a, 1))
+
+
+@pytest.mark.parametrize("which", ["eng16", "eng64"])
+def test_modswitch(which, request):
+    e = request.getfixturevalue(which)
+    o = e.orc
+    for lvl in range(0, o.par.depth - 1):
+        L, H = o.L(lvl), o.H
+        _, raw = rand_poly_raw(o, lvl, 40 + lvl)
+        c = o.crt(raw, lvl)
+        d = e.up(c)
+        e.call("cuhe_mod_switch", p(d), p(d), p(d[L - 1]), lvl, e.st())
+        got = Eng.dn(d, np.uint32)[: L - 1]
+        assert np.array_equal(got, o.modswitch(c, lvl))
+    assert e.lib.cuhe_mod_switch(e.h, p(d), p(d), p(d), o.par.depth - 1, e.st()) != 0   # last level refuses
+
+
+@pytest.mark.parametrize("ps", [SMALL_RELIN, MID32K, MID64K])
+def test_relin(lib, ps):
+    e = Eng(lib, ps)
+    try:
+        o = e.orc
+        K0, W0, H, N = o.par.numEvalKey, o.W(0), o.H, o.N
+        rng = random.Random(11)
+        eks = [o.to_raw([rng.randrange(o.moduli[0]) for _ in range(o.n)], 0) for _ in range(K0)]
+        o.init_relin(eks)
+        d_eks = e.up(np.stack(eks))
+        e.call("cuhe_relin_init", p(d_eks), e.st())
+        for lvl in (0, o.par.depth - 1):
+            L = o.L(lvl)
+            _, raw = rand_poly_raw(o, lvl, 70 + lvl)
+            d_out = e.empty((L, N), np.uint64)
+            e.call("cuhe_relin", p(d_out), p(e.up(raw)), lvl, e.st())
+            want = o.relin_mac(raw, lvl)
+            assert np.array_equal(Eng.dn(d_out, np.uint64), want)
+            # followed by the reference's n2c (isProd=true): inttMod
+            d_c = e.empty((L, H), np.uint32)
+            e.call("cuhe_intt_mod", p(d_c), p(d_out), lvl, e.st())
+            assert np.array_equal(Eng.dn(d_c, np.uint32), o.intt_mod(want))
+    finally:
+        e.close()
+
+
+def test_mul_raw_host_end_to_end(eng16):
+    e, o = eng16, eng16.orc
+    lvl = 0
+    a, ra = rand_poly_raw(o, lvl, 5)
+    b, rb = rand_poly_raw(o, lvl, 6)
+    out = np.zeros_like(ra)
+    e.call("cuhe_mul_raw_host", out.ctypes.data_as(C.c_void_p), ra.ctypes.data_as(C.c_void_p),
+           rb.ctypes.data_as(C.c_void_p), lvl, e.st())
+    assert o.from_raw(out) == o.mul_exact(a, b, lvl)
+
+
+def test_sharded_contexts_match_unsharded(lib):
+    """Residue sharding (rank r of G owns primes r, r+G, ...): two shard
+    contexts on one device reproduce the single-context result row for row."""
+    ps = SIMPLE_DHS
+    full = Eng(lib, ps)
+    shards = [Eng(lib, ps, rank=r, world=2) for r in range(2)]
+    try:
+        o = full.orc
+        lvl = 0
+        L, H, N = o.L(lvl), o.H, o.N
+        _, ra = rand_poly_raw(o, lvl, 21)
+        _, rb = rand_poly_raw(o, lvl, 22)
+        want = o.mul_raw_to_crt(ra, rb, lvl)
+        gathered = np.zeros((L, H), dtype=np.uint32)
+        for r, e in enumerate(shards):
+            rows = e.rows(lvl)
+            assert rows == len(range(r, L, 2))
+            da, db = e.up(ra), e.up(rb)
+            ca, cb = e.empty((rows, H), np.uint32), e.empty((rows, H), np.uint32)
+            e.call("cuhe_crt", p(ca), p(da), lvl, e.st())
+            e.call("cuhe_crt", p(cb), p(db), lvl, e.st())
+            na, nb = e.empty((rows, N), np.uint64), e.empty((rows, N), np.uint64)
+            e.call("cuhe_ntt", p(na), p(ca), lvl, e.st())
+            e.call("cuhe_ntt", p(nb), p(cb), lvl, e.st())
+            out = e.empty((rows, H), np.uint32)
+            e.call("cuhe_ntt_mul_intt_mod", p(out), p(na), p(nb), lvl, e.st())
+            gathered[r::2] = Eng.dn(out, np.uint32)
+        assert np.array_equal(gathered, want)
+        # ICRT on the gathered residues, split by coefficient range across "ranks"
+        W = o.W(lvl)
+        d_all = shards[0].up(gathered)
+        raw = shards[0].empty((H, W), np.uint32)
+        shards[0].call("cuhe_icrt", p(raw), p(d_all), lvl, 0, H // 2, shards[0].st())
+        shards[1].call("cuhe_icrt", p(raw), p(d_all), lvl, H // 2, H, shards[1].st())
+        shards[0].torch.cuda.synchronize()
+        assert np.array_equal(Eng.dn(raw, np.uint32), o.icrt(want, lvl))
+        # modswitch with the dropped row supplied by its owner
+        last_owner = (L - 1) % 2
+        d_last = shards[0].up(want[L - 1])
+        ms = o.modswitch(want, lvl)
+        for r, e in enumerate(shards):
+            loc = e.up(np.ascontiguousarray(want[r::2]))
+            e.call("cuhe_mod_switch", p(loc), p(loc), p(d_last), lvl, e.st())
+            keep = len(range(r, L - 1, 2))
+            assert np.array_equal(Eng.dn(loc, np.uint32)[:keep], ms[r::2])
+        assert last_owner in (0, 1)
+    finally:
+        full.close()
+        for e in shards:
+            e.close()
+
+
+def test_full_size_c2_properties(lib):
+    """BASELINE configs[1] (N=65536, 24 primes): oracle parity on the whole
+    multiply plus size-independent properties (linearity of the transform,
+    NTT/INTT round trip, ICRT o CRT = identity)."""
+    e = Eng(lib, C2)
+    try:
+        o = e.orc
+        lvl = 0
+        L, W, H, N = o.L(lvl), o.W(lvl), o.H, o.N
+        a, ra = rand_poly_raw(o, lvl, 31)
+        b, rb = rand_poly_raw(o, lvl, 32)
+        out = np.zeros_like(ra)
+        e.call("cuhe_mul_raw_host", out.ctypes.data_as(C.c_void_p), ra.ctypes.data_as(C.c_void_p),
+               rb.ctypes.data_as(C.c_void_p), lvl, e.st())
+        want_crt = o.mul_raw_to_crt(ra, rb, lvl)
+        assert np.array_equal(out, o.icrt(want_crt, lvl))
+        # commutativity through the host entry point
+        out2 = np.zeros_like(ra)
+        e.call("cuhe_mul_raw_host", out2.ctypes.data_as(C.c_void_p), rb.ctypes.data_as(C.c_void_p),
+               ra.ctypes.data_as(C.c_void_p), lvl, e.st())
+        assert np.array_equal(out, out2)
+        # CRT -> ICRT identity and NTT linearity on device
+        d_raw = e.up(ra)
+        d_crt = e.empty((L, H), np.uint32)
+        e.call("cuhe_crt", p(d_crt), p(d_raw), lvl, e.st())
+        d_raw2 = e.empty((H, W), np.uint32)
+        e.call("cuhe_icrt", p(d_raw2), p(d_crt), lvl, 0, H, e.st())
+        assert np.array_equal(Eng.dn(d_raw2, np.uint32), ra)
+        d_crtb = e.empty((L, H), np.uint32)
+        e.call("cuhe_crt", p(d_crtb), p(e.up(rb)), lvl, e.st())
+        na, nb, ns = (e.empty((L, N), np.uint64) for _ in range(3))
+        e.call("cuhe_ntt", p(na), p(d_crt), lvl, e.st())
+        e.call("cuhe_ntt", p(nb), p(d_crtb), lvl, e.st())
+        d_sum = e.empty((L, H), np.uint32)
+        e.call("cuhe_crt_add", p(d_sum), p(d_crt), p(d_crtb), lvl, e.st())
+        e.call("cuhe_ntt", p(ns), p(d_sum), lvl, e.st())
+        nab = e.empty((L, N), np.uint64)
+        e.call("cuhe_ntt_add", p(nab), p(na), p(nb), lvl, e.st())
+        # NTT(a+b mod p) differs from NTT(a)+NTT(b) by NTT of the p-multiples; compare after INTT % p
+        c1, c2 = e.empty((L, H), np.uint32), e.empty((L, H), np.uint32)
+        e.call("cuhe_intt", p(c1), p(ns), lvl, e.st())
+        e.call("cuhe_intt", p(c2), p(nab), lvl, e.st())
+        assert np.array_equal(Eng.dn(c1, np.uint32), Eng.dn(c2, np.uint32))
+    finally:
+        e.close()
