@@ -9,7 +9,7 @@ The reference itself cannot be run here (needs NTL; texture references are
 rejected by nvcc 12.9) and stores no vectors, so these fixtures are oracle
 outputs pinned by exact arithmetic, not reference outputs.
 
-    python -m tests.golden.make_golden          # rewrites golden.json
+    python tests/golden/make_golden.py          # rewrites golden.json
 """
 import hashlib
 import json
@@ -20,8 +20,9 @@ import sys
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-if ROOT not in sys.path:
-    sys.path.insert(0, ROOT)
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
 
 CASES = [
     dict(name="simple_dhs_16k", params=[5, 2, 1, 61, 20, 8191], seed=20260924, size="small"),
@@ -44,7 +45,7 @@ def inputs(o, seed, lvl=0):
 
 
 def compute_case(params, seed, exact=False):
-    from tests.conftest import get_oracle
+    from common import get_oracle
     o = get_oracle(tuple(params))
     a, b = inputs(o, seed)
     ra, rb = o.to_raw(a, 0), o.to_raw(b, 0)

@@ -7,7 +7,7 @@ import re
 
 import pytest
 
-from conftest import C2, PRINCE, ROOT, SIMPLE_DHS, SMALL_RELIN, MID32K, MID64K
+from common import C2, PRINCE, ROOT, SIMPLE_DHS, SMALL_RELIN, MID32K, MID64K
 
 
 def _declared_symbols():

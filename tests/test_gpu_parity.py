@@ -9,7 +9,7 @@ import random
 import numpy as np
 import pytest
 
-from conftest import C2, MID32K, MID64K, SIMPLE_DHS, SMALL_RELIN, get_oracle
+from common import C2, MID32K, MID64K, SIMPLE_DHS, SMALL_RELIN, get_oracle
 
 pytestmark = pytest.mark.gpu
 

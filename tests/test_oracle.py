@@ -13,7 +13,7 @@ import random
 import numpy as np
 import pytest
 
-from conftest import C2, PRINCE, ROOT, SIMPLE_DHS, SMALL_RELIN, get_oracle
+from common import C2, PRINCE, ROOT, SIMPLE_DHS, SMALL_RELIN, get_oracle
 
 from oracle import oracle as orc
 from oracle import pyoracle as po
@@ -188,7 +188,11 @@ def test_golden_fixtures():
     (tests/golden/make_golden.py).  Guards the oracle itself against drift."""
     path = os.path.join(ROOT, "tests", "golden", "golden.json")
     g = json.load(open(path))
-    from tests.golden.make_golden import compute_case
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(ROOT, "tests", "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    compute_case = mg.compute_case
     for case in g["cases"]:
         if case["size"] == "full" and not os.environ.get("CUHE_GOLDEN_FULL"):
             continue
