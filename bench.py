@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- homomorphic ctxt x ctxt multiply throughput on B200 (BASELINE.json
+configs[1]: ring degree 2^15 -> NTT length 65536, 24 CRT primes), with the
+64K-point NTT roofline, the end-to-end host-buffer number and the CPU baseline.
+
+  python bench.py --gpus 1 --steps K --warmup W            # our arm
+  python bench.py --impl reference --gpus N --steps K ...  # CPU arm (oracle port)
+  torchrun --nproc-per-node N bench.py --gpus N ...        # residues sharded over N GPUs
+
+A "step" = one batch of B independent ciphertext products, RAW operands
+resident in HBM -> RAW product in HBM (crt x2, forward NTT x2L, fused pointwise
+mul + inverse NTT, polynomial Barrett (2 more forward + 2 more inverse NTTs per
+residue), ICRT).  With N > 1 the CRT-residue axis is sharded (rank r owns primes
+r, r+N, ...), the residues are all-gathered over NCCL before ICRT, ICRT is split
+by coefficient range and the RAW slices are all-gathered again.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import random
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = (24, 2, 16, 24, 24, 32767)      # setParameters(d,p,w,min,cut,m): N=65536, L=24, W=18
+WORKLOAD_NAME = "ctxt x ctxt multiply, ring degree 2^15 (n=27000, nttLen=65536), 24 CRT primes (576-bit q)"
+NTT_BYTES_64K = 655360                      # u32[32768] in + u64[65536] out
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower() == "active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def gen_raw(o, batch, nbuf, seed):
+    """nbuf x batch operand pairs, coefficients uniform in [0, q0): u32[nbuf][batch][H][W]"""
+    rng = random.Random(seed)
+    q0, W, H, n = o["q0"], o["W"], o["H"], o["n"]
+    nb = W * 4
+
+    def poly():
+        body = b"".join(rng.randrange(q0).to_bytes(nb, "little") for _ in range(n))
+        buf = np.zeros(H * W, dtype=np.uint32)
+        buf[: n * W] = np.frombuffer(body, dtype="<u4")
+        return buf.reshape(H, W)
+    # a few distinct polynomials, tiled (content does not change the work)
+    base = [poly() for _ in range(4)]
+    a = np.stack([np.stack([base[(i + j) % 4] for j in range(batch)]) for i in range(nbuf)])
+    b = np.stack([np.stack([base[(i + j + 1) % 4] for j in range(batch)]) for i in range(nbuf)])
+    return a, b
+
+
+# --------------------------------------------------------------------------------
+# CPU arm: the oracle port (the reference's own CPU path is NTL, absent here)
+# --------------------------------------------------------------------------------
+def cpu_mul_rate(min_seconds: float, max_muls: int = 64):
+    from oracle.oracle import Oracle, lib
+    o = Oracle(*WORKLOAD)
+    o.barrett_tables()
+    rng = random.Random(1)
+    q0 = o.moduli[0]
+    a = o.to_raw([rng.randrange(q0) for _ in range(o.n)], 0)
+    b = o.to_raw([rng.randrange(q0) for _ in range(o.n)], 0)
+    o.icrt(o.mul_raw_to_crt(a, b, 0), 0)          # warm-up (page in, build tables)
+    done, t0 = 0, time.perf_counter()
+    while True:
+        o.icrt(o.mul_raw_to_crt(a, b, 0), 0)
+        done += 1
+        el = time.perf_counter() - t0
+        if el >= min_seconds or done >= max_muls:
+            break
+    return done / el, done, el, lib().orc_max_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step = []
+    from oracle.oracle import Oracle, lib
+    o = Oracle(*WORKLOAD)
+    o.barrett_tables()
+    rng = random.Random(1)
+    q0 = o.moduli[0]
+    a = o.to_raw([rng.randrange(q0) for _ in range(o.n)], 0)
+    b = o.to_raw([rng.randrange(q0) for _ in range(o.n)], 0)
+    for _ in range(args.warmup):
+        o.icrt(o.mul_raw_to_crt(a, b, 0), 0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.icrt(o.mul_raw_to_crt(a, b, 0), 0)
+    el = time.perf_counter() - t0
+    val = args.steps / el
+    cores = lib().orc_max_threads()
+    out = {
+        "impl": "reference", "metric": "homomorphic ctxt x ctxt mul/s", "value": val, "unit": "mul/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64 (mod 2^64-2^32+1) / u32 residues",
+        "data": "synthetic", "config": {"workload": WORKLOAD_NAME, "batch": 1},
+        "cpu_baseline": {"value": val, "unit": "mul/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} multiplications, OpenMP over residues; NTL (the reference's CPU path) is not installed"},
+        "e2e": {"value": val, "unit": "mul/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+# --------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from cuhe_b200._lib import check, cuhe_params, load_library
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = load_library()
+    par = cuhe_params()
+    check(lib.cuhe_set_parameters(C.byref(par), *WORKLOAD))
+    h = C.c_void_p()
+    check(lib.cuhe_ctx_create(C.byref(h), C.byref(par), local, rank, world))
+    # Phi_m from the host helper (the caller supplies polyMod, as DHS.cu does)
+    from cuhe_b200.hostmath import cyclotomic
+    phi = np.array(cyclotomic(WORKLOAD[5]), dtype=np.int64)
+    check(lib.cuhe_ctx_set_poly_modulus_host(h, phi.ctypes.data_as(C.c_void_p), len(phi)))
+    L, W, H, N, n = par.numCrtPrime, lib.cuhe_param_words_coeff(C.byref(par), 0), par.crtLen, par.nttLen, par.modLen
+    rows = lib.cuhe_ctx_rows(h, 0)
+    assert L % world == 0, "bench shards need numCrtPrime divisible by the GPU count"
+    qw = np.zeros(W + 1, dtype=np.uint32)
+    check(lib.cuhe_ctx_coeff_modulus_host(h, 0, qw.ctypes.data_as(C.c_void_p), W + 1))
+    info = dict(q0=int.from_bytes(qw.tobytes(), "little"), W=W, H=H, n=n)
+    B, NBUF = args.batch, 4
+    a_np, b_np = gen_raw(info, B, NBUF, 20260924)
+    a_dev = torch.from_numpy(a_np.view(np.int32)).to(dev)
+    b_dev = torch.from_numpy(b_np.view(np.int32)).to(dev)
+    crt_loc = torch.zeros((B, rows, H), dtype=torch.int32, device=dev)
+    crt_all = torch.zeros((B, L, H), dtype=torch.int32, device=dev)
+    gather = torch.zeros((world, B, rows, H), dtype=torch.int32, device=dev) if world > 1 else None
+    raw_out = torch.zeros((B, H, W), dtype=torch.int32, device=dev)
+    Hs = H // world
+    raw_gather = torch.zeros((world, B, Hs, W), dtype=torch.int32, device=dev) if world > 1 else None
+    st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)  # noqa: E731
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+
+    def step(i):
+        k = i % NBUF
+        check(lib.cuhe_mul_crt_batch(h, p(crt_loc), p(a_dev[k]), p(b_dev[k]), 0, B, st()))
+        if world == 1:
+            check(lib.cuhe_icrt_batch(h, p(raw_out), p(crt_loc), 0, 0, H, B, st()))
+        else:
+            dist.all_gather_into_tensor(gather, crt_loc)                 # NCCL over NVLink
+            crt_all.view(B, rows, world, H).copy_(gather.permute(1, 2, 0, 3))   # prime l = r + world*i
+            check(lib.cuhe_icrt_batch(h, p(raw_out), p(crt_all), 0, rank * Hs, (rank + 1) * Hs, B, st()))
+            dist.all_gather_into_tensor(raw_gather, raw_out[:, rank * Hs:(rank + 1) * Hs].contiguous())
+            raw_out.view(B, world, Hs, W).copy_(raw_gather.permute(1, 0, 2, 3))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    lib.cuhe_launch_count(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = int(lib.cuhe_launch_count(0))
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    value = B * args.steps / (ms * 1e-3)
+
+    # ---- roofline: the dominant kernels are the NTT passes; time one batched forward
+    #      64K ext-NTT launch pair (pass 1 + pass 2) alone, inputs larger than L2 ----
+    roof = None
+    ntt_rate = None
+    if rank == 0:
+        cnt = 512
+        src = torch.randint(0, 2**31 - 1, (2, cnt, H), dtype=torch.int32, device=dev)     # 2 x 67 MB
+        dst = torch.zeros((cnt, N), dtype=torch.int64, device=dev)                         # 268 MB
+        for i in range(3):
+            check(lib.cuhe_ntt_ext_batch(h, p(dst), p(src[i % 2]), N, cnt, C.c_longlong(H), st()))
+        torch.cuda.synchronize()
+        reps = 10
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for i in range(reps):
+            check(lib.cuhe_ntt_ext_batch(h, p(dst), p(src[i % 2]), N, cnt, C.c_longlong(H), st()))
+        k1.record()
+        torch.cuda.synchronize()
+        kms = k0.elapsed_time(k1) / reps
+        pk, pk_src = peaks()
+        ach = NTT_BYTES_64K * cnt / (kms * 1e-3) / 1e9
+        ntt_rate = cnt / (kms * 1e-3)
+        roof = {"kernel": "ntt_pass1_kernel<EXT_U32> + ntt_pass2_kernel<16,U64> (one batched forward 64K NTT)",
+                "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                "peak_source": pk_src + " (burst copy bandwidth)", "traffic": None,
+                "algorithmic_bytes_per_launch": NTT_BYTES_64K * cnt, "launch_ms": kms, "batch": cnt,
+                "note": "INT32-ALU bound (SURVEY F9): see DESIGN.md for the instruction-issue roofline"}
+        del src, dst
+
+    # ---- e2e: host buffers through the C ABI (the device part of mulZZX), H2D + D2H inside ----
+    e2e = None
+    if world == 1:
+        ah = torch.from_numpy(a_np[0].view(np.int32)).pin_memory()
+        bh = torch.from_numpy(b_np[0].view(np.int32)).pin_memory()
+        oh = torch.zeros((B, H, W), dtype=torch.int32).pin_memory()
+        for _ in range(2):
+            check(lib.cuhe_mul_raw_host_batch(h, p(oh), p(ah), p(bh), 0, B, st()))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            check(lib.cuhe_mul_raw_host_batch(h, p(oh), p(ah), p(bh), 0, B, st()))
+        torch.cuda.synchronize()
+        el = time.perf_counter() - t0
+        e2e = {"value": B * args.steps / el, "unit": "mul/s", "h2d_bytes_per_step": int(2 * B * H * W * 4),
+               "d2h_bytes_per_step": int(B * H * W * 4), "api": "cuhe_mul_raw_host_batch (pinned host RAW in/out)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, done, el, cores = cpu_mul_rate(10.0)
+        cpu = {"value": v, "unit": "mul/s", "cores": cores, "kind": "port",
+               "sample": f"{done} multiplications of the same workload in {el:.1f} s (C oracle, OpenMP over residues)"}
+
+    if rank == 0:
+        out = {
+            "metric": "homomorphic ctxt x ctxt mul/s", "value": value, "unit": "mul/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u64 (mod 2^64-2^32+1) / u32 residues",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAME, "batch": B, "parallelism": f"residue-shard x{world}" if world > 1 else "single GPU",
+                       "l2": f"{NBUF} rotating operand sets; per-step NTT intermediates {2 * B * L * N * 8 / 1e6:.0f} MB exceed the 126 MB L2"},
+            "ntt_64k_per_s": ntt_rate, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        print(json.dumps(out))
+    lib.cuhe_ctx_destroy(h)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps > 50:
+            args.steps = 50
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcuhe_b200.so")
+LIB_PATH = os.environ.get("CUHE_B200_LIB", os.path.join(_HERE, "libcuhe_b200.so"))   # override: A/B kernel experiments
 
 
 class CuHEError(RuntimeError):
@@ -66,6 +66,9 @@ SYMBOLS = {
     "cuhe_ntt_ext_batch": (_i, [_vp, _vp, _vp, _i, _i, _ll, _vp]),
     "cuhe_intt_batch": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "cuhe_mul_raw_host": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
+    "cuhe_mul_raw_host_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "cuhe_mul_crt_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "cuhe_icrt_batch": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "cuhe_modp_batch": (_i, [_vp, _i, _vp, _vp, _vp, C.c_size_t, _i, _vp]),
     "cuhe_launch_count": (_ll, [_i]),
 }

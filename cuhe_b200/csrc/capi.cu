@@ -166,23 +166,25 @@ static void inv_ntt_modp(cuhe_ctx* c, int N, uint32_t* dst, const uint64_t* src,
     CK(launch_pass2(pl.r3, OUT_U32_MODP, b, count, st));
 }
 
-static void barrett_impl(cuhe_ctx* c, uint32_t* dst, const uint32_t* hold, int lvl, cudaStream_t st) {
+// `batch` polynomials, each `rows` residues: hold u32[batch*rows][N] -> dst u32[batch*rows][H]
+static void barrett_impl(cuhe_ctx* c, uint32_t* dst, const uint32_t* hold, int lvl, int batch, cudaStream_t st) {
     if (!c->have_polymod) throw StateError{"Barrett reduction needs cuhe_ctx_set_poly_modulus_host first"};
     const int N = c->par.nttLen, H = c->par.crtLen, n = c->par.modLen, rows = c->rows(lvl);
-    if (rows == 0) return;
-    Tmp g(c, (size_t)rows * N * 8, st), t(c, (size_t)rows * N * 4, st), s(c, (size_t)rows * N * 4, st);
+    const int cnt = rows * batch;
+    if (cnt == 0) return;
+    Tmp g(c, (size_t)cnt * N * 8, st), t(c, (size_t)cnt * N * 4, st), s(c, (size_t)cnt * N * 4, st);
     // g = NTT(f >> (n-1)) * NTT(u)        (cuhe/Operations.cu:469-474)
-    fwd_ntt(c, N, g.as<uint64_t>(), hold + (n - 1), N, rows, c->d_u_ntt, rows, st);
+    fwd_ntt(c, N, g.as<uint64_t>(), hold + (n - 1), N, cnt, c->d_u_ntt, rows, st);
     // t = INTT(g) % p                      (:475)
-    inv_ntt_modp(c, N, t.as<uint32_t>(), g.as<uint64_t>(), nullptr, rows, rows, st);
+    inv_ntt_modp(c, N, t.as<uint32_t>(), g.as<uint64_t>(), nullptr, cnt, rows, st);
     // g = NTT(t >> n) * NTT(m')            (:478-485)
-    fwd_ntt(c, N, g.as<uint64_t>(), t.as<uint32_t>() + n, N, rows, c->d_m_ntt, rows, st);
+    fwd_ntt(c, N, g.as<uint64_t>(), t.as<uint32_t>() + n, N, cnt, c->d_m_ntt, rows, st);
     // s = INTT(g) % p                      (:489)
-    inv_ntt_modp(c, N, s.as<uint32_t>(), g.as<uint64_t>(), nullptr, rows, rows, st);
+    inv_ntt_modp(c, N, s.as<uint32_t>(), g.as<uint64_t>(), nullptr, cnt, rows, st);
     // out = f - (t on [n,2n)) - s, conditional -m'   (:486-500)
-    dim3 grid((H + 255) / 256, rows);
-    barrett_finish_kernel<<<grid, 256, 0, st>>>(dst, hold, t.as<uint32_t>(), s.as<uint32_t>(), c->d_m_crt, c->pv(), n,
-                                               H, N);
+    dim3 grid((H + 255) / 256, cnt);
+    barrett_finish_kernel<<<grid, 256, 0, st>>>(dst, hold, t.as<uint32_t>(), s.as<uint32_t>(), c->d_m_crt, c->pv(), rows,
+                                               n, H, N);
     count_launch();
     CK(cudaGetLastError());
 }
@@ -226,11 +228,37 @@ __global__ void modp_batch_kernel(int op, uint64_t* __restrict__ out, const uint
 }
 
 template <int WMAX>
-static void launch_icrt(uint32_t* dst, const uint32_t* src, cuhe_ctx* c, const IcrtDev& ic, int b, int e, cudaStream_t st) {
+static void launch_icrt(uint32_t* dst, const uint32_t* src, cuhe_ctx* c, const IcrtDev& ic, int b, int e, int batch,
+                        cudaStream_t st) {
     const int cnt = e - b;
-    icrt_kernel<WMAX><<<(cnt + 127) / 128, 128, 0, st>>>(dst, src, c->d_primes, c->d_mus, ic.M, ic.mi, ic.bi, ic.L, ic.W,
-                                                         ic.Wp, b, e, c->par.crtLen);
+    dim3 grid((cnt + 127) / 128, batch);
+    icrt_kernel<WMAX><<<grid, 128, 0, st>>>(dst, src, c->d_primes, c->d_mus, ic.M, ic.mi, ic.bi, ic.L, ic.W, ic.Wp, b, e,
+                                            c->par.crtLen);
     count_launch();
+}
+// ICRT of `batch` polynomials: crt_all u32[batch][L][H] -> raw u32[batch][H][W], coefficients [b,e)
+static void do_icrt(cuhe_ctx* c, uint32_t* raw_out, const uint32_t* crt_all, int lvl, int b, int e, int batch,
+                    cudaStream_t st) {
+    if (e > c->par.modLen) e = c->par.modLen;     // the reference writes idx < modLen only
+    if (b >= e || batch <= 0) return;
+    const IcrtDev& ic = c->icrt[lvl];
+    if (ic.W <= 8) launch_icrt<8>(raw_out, crt_all, c, ic, b, e, batch, st);
+    else if (ic.W <= 20) launch_icrt<20>(raw_out, crt_all, c, ic, b, e, batch, st);
+    else if (ic.W <= 36) launch_icrt<36>(raw_out, crt_all, c, ic, b, e, batch, st);
+    else if (ic.W <= 52) launch_icrt<52>(raw_out, crt_all, c, ic, b, e, batch, st);
+    else if (ic.W <= 104) launch_icrt<104>(raw_out, crt_all, c, ic, b, e, batch, st);
+    else throw ArgError{"coefficient modulus wider than 104 words"};
+    CK(cudaGetLastError());
+}
+// CRT of `batch` polynomials: raw u32[batch][H][W] -> dst u32[batch][rows][H]
+static void do_crt(cuhe_ctx* c, uint32_t* dst, const uint32_t* raw, int lvl, int batch, cudaStream_t st) {
+    const int rows = c->rows(lvl), W = c->par.wordsCoeffAt(lvl), H = c->par.crtLen;
+    if (rows == 0 || batch <= 0) return;
+    const size_t smem = (size_t)kCrtThreads * (W | 1) * 4;
+    dim3 grid((H + kCrtThreads - 1) / kCrtThreads, batch);
+    crt_kernel<<<grid, kCrtThreads, smem, st>>>(dst, raw, c->pv(), rows, c->d_pow32, c->pow_stride, W, c->par.modLen, H);
+    count_launch();
+    CK(cudaGetLastError());
 }
 
 }  // namespace cuhe_b200
@@ -460,13 +488,7 @@ int cuhe_crt(cuhe_ctx* c, uint32_t* dst, const uint32_t* raw, int lvl, cuhe_stre
     return guarded([&] {
         check_lvl(c, lvl); REQUIRE(dst && raw, "null pointer");
         DeviceGuard dg(c->device);
-        const int rows = c->rows(lvl), W = c->par.wordsCoeffAt(lvl), H = c->par.crtLen;
-        if (rows == 0) return;
-        const size_t smem = (size_t)kCrtThreads * (W | 1) * 4;
-        crt_kernel<<<(H + kCrtThreads - 1) / kCrtThreads, kCrtThreads, smem, (cudaStream_t)stream>>>(
-            dst, raw, c->pv(), rows, c->d_pow32, c->pow_stride, W, c->par.modLen, H);
-        count_launch();
-        CK(cudaGetLastError());
+        do_crt(c, dst, raw, lvl, 1, (cudaStream_t)stream);
     });
 }
 
@@ -475,17 +497,7 @@ int cuhe_icrt(cuhe_ctx* c, uint32_t* raw_out, const uint32_t* crt_all, int lvl, 
         check_lvl(c, lvl); REQUIRE(raw_out && crt_all, "null pointer");
         REQUIRE(0 <= b && b <= e && e <= c->par.crtLen, "coefficient range out of bounds");
         DeviceGuard dg(c->device);
-        if (e > c->par.modLen) e = c->par.modLen;     // the reference writes idx < modLen only
-        if (b >= e) return;
-        const IcrtDev& ic = c->icrt[lvl];
-        cudaStream_t st = (cudaStream_t)stream;
-        if (ic.W <= 8) launch_icrt<8>(raw_out, crt_all, c, ic, b, e, st);
-        else if (ic.W <= 20) launch_icrt<20>(raw_out, crt_all, c, ic, b, e, st);
-        else if (ic.W <= 36) launch_icrt<36>(raw_out, crt_all, c, ic, b, e, st);
-        else if (ic.W <= 52) launch_icrt<52>(raw_out, crt_all, c, ic, b, e, st);
-        else if (ic.W <= 104) launch_icrt<104>(raw_out, crt_all, c, ic, b, e, st);
-        else throw ArgError{"coefficient modulus wider than 104 words"};
-        CK(cudaGetLastError());
+        do_icrt(c, raw_out, crt_all, lvl, b, e, 1, (cudaStream_t)stream);
     });
 }
 
@@ -523,29 +535,45 @@ int cuhe_barrett(cuhe_ctx* c, uint32_t* dst, const uint32_t* hold, int lvl, cuhe
     return guarded([&] {
         check_lvl(c, lvl); REQUIRE(dst && hold, "null pointer");
         DeviceGuard dg(c->device);
-        barrett_impl(c, dst, hold, lvl, (cudaStream_t)stream);
+        barrett_impl(c, dst, hold, lvl, 1, (cudaStream_t)stream);
     });
 }
-static void intt_mod_impl(cuhe_ctx* c, uint32_t* dst, const uint64_t* x, const uint64_t* y, int lvl, cudaStream_t st) {
+static void intt_mod_impl(cuhe_ctx* c, uint32_t* dst, const uint64_t* x, const uint64_t* y, int lvl, int batch,
+                          cudaStream_t st) {
     const int rows = c->rows(lvl), N = c->par.nttLen;
-    if (rows == 0) return;
+    if (rows * batch == 0) return;
     if (!c->have_polymod) throw StateError{"Barrett reduction needs cuhe_ctx_set_poly_modulus_host first"};
-    Tmp hold(c, (size_t)rows * N * 4, st);
-    inv_ntt_modp(c, N, hold.as<uint32_t>(), x, y, rows, rows, st);
-    barrett_impl(c, dst, hold.as<uint32_t>(), lvl, st);
+    Tmp hold(c, (size_t)rows * batch * N * 4, st);
+    inv_ntt_modp(c, N, hold.as<uint32_t>(), x, y, rows * batch, rows, st);
+    barrett_impl(c, dst, hold.as<uint32_t>(), lvl, batch, st);
+}
+// raw a,b u32[batch][H][W] (device) -> product residues u32[batch][rows][H]
+static void mul_crt_batch_impl(cuhe_ctx* c, uint32_t* dst, const uint32_t* a_raw, const uint32_t* b_raw, int lvl, int batch,
+                               cudaStream_t st) {
+    const int rows = c->rows(lvl), H = c->par.crtLen, N = c->par.nttLen;
+    const int cnt = rows * batch;
+    if (cnt == 0) return;
+    Tmp cab(c, (size_t)2 * cnt * H * 4, st), nab(c, (size_t)2 * cnt * N * 8, st);
+    uint32_t* ca = cab.as<uint32_t>();
+    uint32_t* cb = ca + (size_t)cnt * H;
+    do_crt(c, ca, a_raw, lvl, batch, st);
+    do_crt(c, cb, b_raw, lvl, batch, st);
+    uint64_t* na = nab.as<uint64_t>();
+    fwd_ntt(c, N, na, ca, H, 2 * cnt, nullptr, 1, st);          // both operands, one launch per pass
+    intt_mod_impl(c, dst, na, na + (size_t)cnt * N, lvl, batch, st);
 }
 int cuhe_intt_mod(cuhe_ctx* c, uint32_t* dst, const uint64_t* src, int lvl, cuhe_stream stream) {
     return guarded([&] {
         check_lvl(c, lvl); REQUIRE(dst && src, "null pointer");
         DeviceGuard dg(c->device);
-        intt_mod_impl(c, dst, src, nullptr, lvl, (cudaStream_t)stream);
+        intt_mod_impl(c, dst, src, nullptr, lvl, 1, (cudaStream_t)stream);
     });
 }
 int cuhe_ntt_mul_intt_mod(cuhe_ctx* c, uint32_t* dst, const uint64_t* x, const uint64_t* y, int lvl, cuhe_stream stream) {
     return guarded([&] {
         check_lvl(c, lvl); REQUIRE(dst && x && y, "null pointer");
         DeviceGuard dg(c->device);
-        intt_mod_impl(c, dst, x, y, lvl, (cudaStream_t)stream);
+        intt_mod_impl(c, dst, x, y, lvl, 1, (cudaStream_t)stream);
     });
 }
 
@@ -621,12 +649,8 @@ int cuhe_relin_init(cuhe_ctx* c, const uint32_t* evalkeys_raw, cuhe_stream strea
         CK(cudaMalloc(&c->d_ek, std::max<size_t>(1, (size_t)rows * K * N * 8)));
         if (rows == 0) return;
         Tmp crt(c, (size_t)rows * H * 4, st), ntt(c, (size_t)rows * N * 8, st);
-        const size_t smem = (size_t)kCrtThreads * (W | 1) * 4;
         for (int k = 0; k < K; k++) {
-            crt_kernel<<<(H + kCrtThreads - 1) / kCrtThreads, kCrtThreads, smem, st>>>(
-                crt.as<uint32_t>(), evalkeys_raw + (size_t)k * H * W, c->pv(), rows, c->d_pow32, c->pow_stride, W,
-                c->par.modLen, H);
-            CK(cudaGetLastError());
+            do_crt(c, crt.as<uint32_t>(), evalkeys_raw + (size_t)k * H * W, 0, 1, st);
             fwd_ntt(c, N, ntt.as<uint64_t>(), crt.as<uint32_t>(), H, rows, nullptr, 1, st);
             // ek[r][k][.] <- ntt[r][.]
             CK(cudaMemcpy2DAsync(c->d_ek + (size_t)k * N, (size_t)K * N * 8, ntt.as<uint64_t>(), (size_t)N * 8, (size_t)N * 8,
@@ -698,38 +722,46 @@ int cuhe_modp_batch(cuhe_ctx* c, int op, uint64_t* out, const uint64_t* x, const
     });
 }
 
+int cuhe_mul_crt_batch(cuhe_ctx* c, uint32_t* dst_crt, const uint32_t* a_raw, const uint32_t* b_raw, int lvl, int batch,
+                       cuhe_stream stream) {
+    return guarded([&] {
+        check_lvl(c, lvl); REQUIRE(dst_crt && a_raw && b_raw, "null pointer");
+        REQUIRE(batch >= 0 && (long long)batch * 2 * c->rows(lvl) <= 65535, "batch too large");
+        DeviceGuard dg(c->device);
+        mul_crt_batch_impl(c, dst_crt, a_raw, b_raw, lvl, batch, (cudaStream_t)stream);
+    });
+}
+int cuhe_icrt_batch(cuhe_ctx* c, uint32_t* raw_out, const uint32_t* crt_all, int lvl, int b, int e, int batch,
+                    cuhe_stream stream) {
+    return guarded([&] {
+        check_lvl(c, lvl); REQUIRE(raw_out && crt_all, "null pointer");
+        REQUIRE(0 <= b && b <= e && e <= c->par.crtLen, "coefficient range out of bounds");
+        REQUIRE(batch >= 0 && batch <= 65535, "batch too large");
+        DeviceGuard dg(c->device);
+        do_icrt(c, raw_out, crt_all, lvl, b, e, batch, (cudaStream_t)stream);
+    });
+}
+
 int cuhe_mul_raw_host(cuhe_ctx* c, uint32_t* out_h, const uint32_t* a_h, const uint32_t* b_h, int lvl, cuhe_stream stream) {
+    return cuhe_mul_raw_host_batch(c, out_h, a_h, b_h, lvl, 1, stream);
+}
+int cuhe_mul_raw_host_batch(cuhe_ctx* c, uint32_t* out_h, const uint32_t* a_h, const uint32_t* b_h, int lvl, int batch,
+                            cuhe_stream stream) {
     return guarded([&] {
         check_lvl(c, lvl); REQUIRE(out_h && a_h && b_h, "null pointer");
         REQUIRE(c->world == 1, "cuhe_mul_raw_host needs an unsharded context");
+        REQUIRE(batch >= 1 && (long long)batch * 2 * c->L(lvl) <= 65535, "bad batch");
         DeviceGuard dg(c->device);
         cudaStream_t st = (cudaStream_t)stream;
-        const int L = c->L(lvl), W = c->par.wordsCoeffAt(lvl), H = c->par.crtLen, N = c->par.nttLen;
-        const size_t raw_b = (size_t)H * W * 4;
-        Tmp ra(c, raw_b, st), rb(c, raw_b, st), ca(c, (size_t)L * H * 4, st), cb(c, (size_t)L * H * 4, st);
-        Tmp na(c, (size_t)L * N * 8, st), nb(c, (size_t)L * N * 8, st);
+        const int L = c->L(lvl), W = c->par.wordsCoeffAt(lvl), H = c->par.crtLen;
+        const size_t raw_b = (size_t)batch * H * W * 4;
+        Tmp ra(c, raw_b, st), rb(c, raw_b, st), cc(c, (size_t)batch * L * H * 4, st);
         CK(cudaMemcpyAsync(ra.p, a_h, raw_b, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(rb.p, b_h, raw_b, cudaMemcpyHostToDevice, st));
-        const size_t smem = (size_t)kCrtThreads * (W | 1) * 4;
-        const int cg = (H + kCrtThreads - 1) / kCrtThreads;
-        crt_kernel<<<cg, kCrtThreads, smem, st>>>(ca.as<uint32_t>(), ra.as<uint32_t>(), c->pv(), L, c->d_pow32, c->pow_stride, W, c->par.modLen, H);
-        count_launch();
-        crt_kernel<<<cg, kCrtThreads, smem, st>>>(cb.as<uint32_t>(), rb.as<uint32_t>(), c->pv(), L, c->d_pow32, c->pow_stride, W, c->par.modLen, H);
-        count_launch();
-        CK(cudaGetLastError());
-        fwd_ntt(c, N, na.as<uint64_t>(), ca.as<uint32_t>(), H, L, nullptr, 1, st);
-        fwd_ntt(c, N, nb.as<uint64_t>(), cb.as<uint32_t>(), H, L, nullptr, 1, st);
-        intt_mod_impl(c, ca.as<uint32_t>(), na.as<uint64_t>(), nb.as<uint64_t>(), lvl, st);
+        mul_crt_batch_impl(c, cc.as<uint32_t>(), ra.as<uint32_t>(), rb.as<uint32_t>(), lvl, batch, st);
         // c2r + r2z (cuhe/CuHE.cu:366-382, 333-348)
         CK(cudaMemsetAsync(ra.p, 0, raw_b, st));
-        const IcrtDev& ic = c->icrt[lvl];
-        const int e = c->par.modLen;
-        if (ic.W <= 8) launch_icrt<8>(ra.as<uint32_t>(), ca.as<uint32_t>(), c, ic, 0, e, st);
-        else if (ic.W <= 20) launch_icrt<20>(ra.as<uint32_t>(), ca.as<uint32_t>(), c, ic, 0, e, st);
-        else if (ic.W <= 36) launch_icrt<36>(ra.as<uint32_t>(), ca.as<uint32_t>(), c, ic, 0, e, st);
-        else if (ic.W <= 52) launch_icrt<52>(ra.as<uint32_t>(), ca.as<uint32_t>(), c, ic, 0, e, st);
-        else launch_icrt<104>(ra.as<uint32_t>(), ca.as<uint32_t>(), c, ic, 0, e, st);
-        CK(cudaGetLastError());
+        do_icrt(c, ra.as<uint32_t>(), cc.as<uint32_t>(), lvl, 0, c->par.modLen, batch, st);
         CK(cudaMemcpyAsync(out_h, ra.p, raw_b, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
     });

@@ -54,6 +54,11 @@ __device__ __forceinline__ void dif_stage(uint64_t (&x)[N], std::integer_sequenc
 template <int N, int H, bool HALF>
 __device__ __forceinline__ void dif_rec(uint64_t (&x)[N]) {
     dif_stage<N, H, HALF>(x, std::make_integer_sequence<int, N / 2>{});
+#ifdef CUHE_STAGE_SYNC
+    // keep the warps of a CTA inside the same window of this long straight-line code so
+    // instruction-cache lines are fetched once per CTA, not once per warp
+    if constexpr (N == 64) __syncthreads();
+#endif
     if constexpr (H > 1) dif_rec<N, H / 2, false>(x);
 }
 // HALF_INPUT: x[N/2..N) are known to be zero (the zero-padded "ext" transform)
@@ -72,8 +77,11 @@ __host__ __device__ constexpr int ilog2(int v) { return v <= 1 ? 0 : 1 + ilog2(v
 // pass 1
 // ---------------------------------------------------------------------------
 
+#ifndef CUHE_P1_THREADS
+#define CUHE_P1_THREADS 128
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(128) ntt_pass1_kernel(Pass1Args a) {
+__global__ void __launch_bounds__(CUHE_P1_THREADS) ntt_pass1_kernel(Pass1Args a) {
     const int j2 = blockIdx.x * blockDim.x + threadIdx.x;
     const int t = blockIdx.y;
     const int n2 = a.n2;

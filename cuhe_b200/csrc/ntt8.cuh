@@ -1,0 +1,210 @@
+// cuhe_b200/csrc/ntt8.cuh
+// NTT pass kernels, generation 2: the same two-pass decomposition as ntt.cuh
+//   N = 64 * N2,  N2 = 64 * R3,  R3 in {4, 8, 16}
+// but every 64-point column transform is run as 8 x 8: two layers of radix-8
+// register butterflies, the column itself parked in a thread-private strip of
+// shared memory between the layers.  Rationale (profiles/r01_ntt_v1_*): the
+// fully unrolled radix-64 of ntt.cuh is ~8100 SASS instructions (130 KB) per
+// kernel, larger than the instruction caches, and ncu attributes most issue
+// stalls to "no_instruction"; it also needs ~200 registers (8 warps/SM).
+// Here the loop bodies are one radix-8 (compile-time shift twiddles) plus a
+// warp-uniform switch over the 8 inter-layer twiddle patterns 2^(3*i*a), so
+// the hot code is ~20 KB and a thread needs ~64 registers.
+//
+// Lanes always run along independent columns, so every shift amount is either a
+// compile-time constant or uniform across the warp -- the per-thread `switch`
+// of the reference's _ls_modP (cuhe/ModP.h:68-229) never appears.
+#pragma once
+#include <cstdint>
+#include <utility>
+#include "engine.hpp"
+#include "modp.cuh"
+#include "ntt.cuh"
+
+namespace cuhe_b200 {
+
+// x[r] *= 2^(3 * I * bitrev3(r)): the twiddle between the two radix-8 layers
+template <int I, int... R>
+__device__ __forceinline__ void twiddle8_seq(uint64_t (&x)[8], std::integer_sequence<int, R...>) {
+    ((x[R] = shl_modP<(3 * I * bitrev(R, 3)) % 192>(x[R])), ...);
+}
+template <int I>
+__device__ __forceinline__ void twiddle8(uint64_t (&x)[8]) {
+    twiddle8_seq<I>(x, std::make_integer_sequence<int, 8>{});
+}
+// i is uniform across the warp (it is a loop counter), so this is a plain jump
+__device__ __forceinline__ void twiddle8_dyn(uint64_t (&x)[8], int i) {
+    switch (i) {
+        case 1: twiddle8<1>(x); break;
+        case 2: twiddle8<2>(x); break;
+        case 3: twiddle8<3>(x); break;
+        case 4: twiddle8<4>(x); break;
+        case 5: twiddle8<5>(x); break;
+        case 6: twiddle8<6>(x); break;
+        case 7: twiddle8<7>(x); break;
+        default: break;
+    }
+}
+
+#ifndef CUHE_P1V2_THREADS
+#define CUHE_P1V2_THREADS 128
+#endif
+
+// ---------------------------------------------------------------------------
+// pass 1: one thread per column j2, 64-point transform over j1 (stride N2) as
+// 8 x 8, then the table multiply by w^(k1*j2).
+//   X[a + 8b] = sum_i w8^(ib) * 2^(3ia) * sum_k x[i + 8k] w8^(ka)
+// ---------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(CUHE_P1V2_THREADS) ntt_pass1_v2_kernel(Pass1Args a) {
+    constexpr int T = CUHE_P1V2_THREADS;
+    constexpr bool EXT = (MODE == IN_EXT_U32 || MODE == IN_DIGIT);
+    extern __shared__ uint64_t S8[];                 // [64][T], column of thread tid at S8[.][tid]
+    const int tid = threadIdx.x;
+    const int j2 = blockIdx.x * T + tid;
+    const int t = blockIdx.y;
+    const int n2 = a.n2;
+    const int N = n2 * 64;
+    uint64_t* col = S8 + tid;
+
+    // digit extraction state (IN_DIGIT), cuhe/Base.cu:361-371
+    int dg_lo = 0, dg_sh = 0; bool dg_two = false; uint64_t dg_mask = 0;
+    if constexpr (MODE == IN_DIGIT) {
+        const int bit = a.digit_w * (a.digit_first + t);
+        dg_lo = bit >> 5; dg_sh = bit & 31;
+        dg_two = (dg_lo + 1) < a.digit_words;
+        dg_mask = (1ull << a.digit_w) - 1;
+    }
+#pragma unroll 1
+    for (int i = 0; i < 8; i++) {
+        uint64_t x[8];
+        if constexpr (MODE == IN_EXT_U32) {
+            const uint32_t* s = (const uint32_t*)a.src + (long long)t * a.src_stride + j2;
+#pragma unroll
+            for (int k = 0; k < 4; k++) x[k] = __ldg(s + (long long)(i + 8 * k) * n2);
+        } else if constexpr (MODE == IN_DIGIT) {
+            const uint32_t* s = (const uint32_t*)a.src;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t* c = s + ((long long)(i + 8 * k) * n2 + j2) * a.digit_words + dg_lo;
+                uint64_t v = __ldg(c);
+                if (dg_two) v |= (uint64_t)__ldg(c + 1) << 32;
+                x[k] = (v >> dg_sh) & dg_mask;
+            }
+        } else {
+            const uint64_t* s = (const uint64_t*)a.src + (long long)t * a.src_stride;
+            const uint64_t* s2 = (const uint64_t*)a.src2 + (long long)t * a.src2_stride;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int e = (N - ((i + 8 * k) * n2 + j2)) & (N - 1);
+                uint64_t v = __ldg(s + e);
+                if constexpr (MODE == IN_U64_REV_MUL) v = mul_modP(v, __ldg(s2 + e));
+                x[k] = v;
+            }
+        }
+        ntt_regs<8, EXT>(x);                         // over k -> a = bitrev3(r)
+        twiddle8_dyn(x, i);                          // * 2^(3*i*a)
+#pragma unroll
+        for (int r = 0; r < 8; r++) col[(bitrev(r, 3) * 8 + i) * T] = x[r];
+    }
+    uint64_t* d = a.scratch + (long long)t * N + j2;
+    const uint64_t* tw = a.tw1 + j2;
+#pragma unroll 1
+    for (int aa = 0; aa < 8; aa++) {
+        uint64_t x[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) x[i] = col[(aa * 8 + i) * T];
+        ntt_regs<8, false>(x);                       // over i -> b = bitrev3(r)
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const int k1 = aa + 8 * bitrev(r, 3);
+            d[(long long)k1 * n2] = mul_modP(x[r], __ldg(tw + (long long)k1 * n2));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// pass 2: CTA = tile of R = 128/R3 rows k1 (contiguous N2 words each).
+//  phase A  thread (row, j2b): 64-point transform over j2a (stride R3) as 8 x 8,
+//           in place in the padded shared tile, then * w_N2^(k2a*j2b)
+//  phase B  thread (row, position): R3-point register transform over j2b and the
+//           natural-order scatter X[k1 + 64*(k2a + 64*k2b)], lanes along k1
+// The phase-A result for k2a = a + 8b sits at position a*8 + b of its column.
+// ---------------------------------------------------------------------------
+template <int R3, int OUT>
+__global__ void __launch_bounds__(128) ntt_pass2_v2_kernel(Pass2Args a) {
+    using Cfg = Pass2Cfg<R3>;
+    constexpr int R = Cfg::R, KS = Cfg::KS, RS = Cfg::RS;
+    constexpr int N2 = 64 * R3, N = 64 * N2;
+    extern __shared__ uint64_t sm[];
+    const int t = blockIdx.y;
+    const int r0 = blockIdx.x * R;
+    const int tid = threadIdx.x;
+    {
+        const int j2b = tid % R3, row = tid / R3;
+        const uint64_t* s = a.scratch + (long long)t * N + (long long)(r0 + row) * N2 + j2b;
+        uint64_t* col = sm + row * RS + j2b;
+#pragma unroll 1
+        for (int i = 0; i < 8; i++) {
+            uint64_t x[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) x[k] = s[(i + 8 * k) * R3];
+            ntt_regs<8, false>(x);
+            twiddle8_dyn(x, i);
+#pragma unroll
+            for (int r = 0; r < 8; r++) col[(bitrev(r, 3) * 8 + i) * KS] = x[r];
+        }
+        const uint64_t* tw = a.tw2 + j2b;
+#pragma unroll 1
+        for (int aa = 0; aa < 8; aa++) {
+            uint64_t x[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) x[i] = col[(aa * 8 + i) * KS];
+            ntt_regs<8, false>(x);
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const int b = bitrev(r, 3);
+                const int k2a = aa + 8 * b;
+                col[(aa * 8 + b) * KS] = mul_modP(x[r], __ldg(tw + k2a * R3));
+            }
+        }
+    }
+    __syncthreads();
+    {
+        constexpr int RL = R < 8 ? R : 8;
+        constexpr int NG = 128 / RL;
+        const int row_lo = tid % RL, g = tid / RL;
+        const int trow = t % a.row_mod;
+        const int pidx = a.prime_base + a.prime_step * trow;
+        uint32_t p = 0; uint64_t mu = 0;
+        if constexpr (OUT == OUT_U32_MODP) { p = a.primes[pidx]; mu = a.mus[pidx]; }
+#pragma unroll 1
+        for (int it = 0; it < (R * 64) / 128; it++) {
+            const int unit = it * NG + g;
+            const int pos = unit % 64;                    // storage position inside the column
+            const int k2a = (pos % 8) * 8 + pos / 8;     // ... holds frequency k2a = a + 8b at a*8+b
+            const int row = (unit / 64) * RL + row_lo;
+            const uint64_t* in = sm + row * RS + pos * KS;
+            uint64_t y[R3];
+#pragma unroll
+            for (int j = 0; j < R3; j++) y[j] = in[j];
+            ntt_regs<R3, false>(y);
+            const long long k1 = r0 + row;
+#pragma unroll
+            for (int i = 0; i < R3; i++) {
+                const int k2b = bitrev(i, ilog2(R3));
+                const long long k = k1 + 64ll * (k2a + 64 * k2b);
+                if constexpr (OUT == OUT_U64) {
+                    ((uint64_t*)a.dst)[(long long)t * a.dst_stride + k] = y[i];
+                } else if constexpr (OUT == OUT_U64_MUL) {
+                    uint64_t m = __ldg(a.mul_tab + (long long)trow * N + k);
+                    ((uint64_t*)a.dst)[(long long)t * a.dst_stride + k] = mul_modP(y[i], m);
+                } else {
+                    ((uint32_t*)a.dst)[(long long)t * a.dst_stride + k] = mod_u64_u32(y[i], p, mu);
+                }
+            }
+        }
+    }
+}
+
+}  // namespace cuhe_b200

@@ -2,13 +2,34 @@
 #include <cuda_runtime.h>
 #include "engine.hpp"
 #include "ntt.cuh"
+#include "ntt8.cuh"
 
 namespace cuhe_b200 {
 
+static cudaError_t set_smem_once(const void* fn, int bytes, bool* done) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !done[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e != cudaSuccess) return e;
+        done[dev] = true;
+    }
+    return cudaSuccess;
+}
+
 template <int MODE>
 static cudaError_t launch_p1(const Pass1Args& a, int count, cudaStream_t st) {
-    dim3 grid(a.n2 / 128, count);
-    ntt_pass1_kernel<MODE><<<grid, 128, 0, st>>>(a);
+#ifdef CUHE_NTT_V1
+    dim3 grid(a.n2 / CUHE_P1_THREADS, count);
+    ntt_pass1_kernel<MODE><<<grid, CUHE_P1_THREADS, 0, st>>>(a);
+#else
+    static bool done[64] = {false};
+    constexpr int smem = 64 * CUHE_P1V2_THREADS * 8;
+    cudaError_t e = set_smem_once((const void*)ntt_pass1_v2_kernel<MODE>, smem, done);
+    if (e != cudaSuccess) return e;
+    dim3 grid(a.n2 / CUHE_P1V2_THREADS, count);
+    ntt_pass1_v2_kernel<MODE><<<grid, CUHE_P1V2_THREADS, smem, st>>>(a);
+#endif
     count_launch();
     return cudaGetLastError();
 }
@@ -27,17 +48,16 @@ cudaError_t launch_pass1(int mode, const Pass1Args& a, int count, cudaStream_t s
 template <int R3, int OUT>
 static cudaError_t launch_p2(const Pass2Args& a, int count, cudaStream_t st) {
     using Cfg = Pass2Cfg<R3>;
-    static bool attr_set[64] = {false};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 64 && !attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(ntt_pass2_kernel<R3, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             Cfg::SMEM);
-        if (e != cudaSuccess) return e;
-        attr_set[dev] = true;
-    }
+    static bool done[64] = {false};
+#ifdef CUHE_NTT_V1
+    auto* fn = ntt_pass2_kernel<R3, OUT>;
+#else
+    auto* fn = ntt_pass2_v2_kernel<R3, OUT>;
+#endif
+    cudaError_t e = set_smem_once((const void*)fn, Cfg::SMEM, done);
+    if (e != cudaSuccess) return e;
     dim3 grid(64 / Cfg::R, count);
-    ntt_pass2_kernel<R3, OUT><<<grid, 128, Cfg::SMEM, st>>>(a);
+    fn<<<grid, 128, Cfg::SMEM, st>>>(a);
     count_launch();
     return cudaGetLastError();
 }

@@ -32,6 +32,8 @@ crt_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ raw, PrimeVi
     const int ws = W | 1;                 // odd stride: conflict-free column reads
     const int i0 = blockIdx.x * kCrtThreads;
     const int cnt = min(kCrtThreads, H - i0);
+    raw += (long long)blockIdx.y * H * W;          // batch
+    dst += (long long)blockIdx.y * rows * H;
     for (int e = threadIdx.x; e < cnt * W; e += kCrtThreads) {
         int c = e / W, k = e - c * W;
         sw[c * ws + k] = raw[(long long)i0 * W + e];
@@ -75,6 +77,8 @@ icrt_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, const 
             const uint32_t* __restrict__ bi, int L, int W, int Wp, int i_begin, int i_end, int H) {
     const int idx = i_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= i_end) return;
+    src += (long long)blockIdx.y * L * H;           // batch
+    dst += (long long)blockIdx.y * H * W;
     uint32_t sum[WMAX + 1];
 #pragma unroll
     for (int k = 0; k <= WMAX; k++) sum[k] = 0;
@@ -204,11 +208,12 @@ __global__ void crt_add_int_kernel(uint32_t* __restrict__ y, const uint32_t* __r
 __global__ void __launch_bounds__(256)
 barrett_finish_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ hold, const uint32_t* __restrict__ t,
                       const uint32_t* __restrict__ s, const uint32_t* __restrict__ m_crt, PrimeView pv,
-                      int n, int H, int N) {
+                      int row_mod, int n, int H, int N) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = blockIdx.y;
+    const int r = blockIdx.y;                   // row of the batch: polynomial r / row_mod, residue r % row_mod
     if (i >= H) return;
-    const int l = prime_index(pv, r);
+    const int lr = r % row_mod;
+    const int l = prime_index(pv, lr);
     const uint32_t p = pv.p[l];
     const long long base = (long long)r * N;
     auto subp = [p](uint32_t a, uint32_t b) { if (a < b) a += p; return a - b; };
@@ -220,7 +225,7 @@ barrett_finish_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ h
     uint32_t v = val(i);
     if (i < n - 1) {
         const uint32_t flag = val(n);
-        if (flag > 0) v = subp(v, m_crt[(long long)r * H + i]);
+        if (flag > 0) v = subp(v, m_crt[(long long)lr * H + i]);
     }
     out[(long long)r * H + i] = v;
 }

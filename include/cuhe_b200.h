@@ -162,6 +162,20 @@ int cuhe_intt_batch(cuhe_ctx* ctx, uint64_t* dst, const uint64_t* src, int nttLe
  * Single-shard contexts only.  Synchronous on return. */
 int cuhe_mul_raw_host(cuhe_ctx* ctx, uint32_t* out_raw_host, const uint32_t* a_raw_host,
                       const uint32_t* b_raw_host, int lvl, cuhe_stream stream);
+/* `batch` independent products in one call: arrays are [batch][crtLen][words(lvl)] */
+int cuhe_mul_raw_host_batch(cuhe_ctx* ctx, uint32_t* out_raw_host, const uint32_t* a_raw_host,
+                            const uint32_t* b_raw_host, int lvl, int batch, cuhe_stream stream);
+
+/* ---- batched device-resident hot path: `batch` independent ciphertext products
+ *      per call, so one launch covers every {CRT prime x ciphertext} transform.
+ *      x2n(a); x2n(b); cAnd; x2c of cuhe/CuHE.cu:259-267 for each pair:
+ *      a_raw,b_raw u32[batch][crtLen][words(lvl)] -> dst_crt u32[batch][rows][crtLen] */
+int cuhe_mul_crt_batch(cuhe_ctx* ctx, uint32_t* dst_crt, const uint32_t* a_raw, const uint32_t* b_raw, int lvl,
+                       int batch, cuhe_stream stream);
+/* icrt() for `batch` polynomials: crt_all u32[batch][numCrtPrime(lvl)][crtLen] ->
+ * raw_out u32[batch][crtLen][words(lvl)], coefficients [coef_begin, coef_end) */
+int cuhe_icrt_batch(cuhe_ctx* ctx, uint32_t* raw_out, const uint32_t* crt_all, int lvl, int coef_begin, int coef_end,
+                    int batch, cuhe_stream stream);
 
 /* ---- device mod-P primitives on arrays: what tests/test_ModP.cu:57-137 drives
  *      (_add/_sub/_mul/_ls_modP of cuhe/ModP.h:68-289).  op: 0 add, 1 sub, 2 mul,

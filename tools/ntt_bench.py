@@ -1,0 +1,55 @@
+#!/usr/bin/env python
+"""Micro-benchmark of the batched transforms through the C ABI (CUDA events on
+the launching stream; inputs + outputs larger than L2).  Used for A/B runs of
+kernel variants: CUHE_B200_LIB=<path to .so> python tools/ntt_bench.py"""
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+from cuhe_b200._lib import LIB_PATH, check, cuhe_params, load_library  # noqa: E402
+
+
+def main():
+    lib = load_library()
+    par = cuhe_params()
+    check(lib.cuhe_set_parameters(C.byref(par), 24, 2, 16, 24, 24, 32767))
+    h = C.c_void_p()
+    check(lib.cuhe_ctx_create(C.byref(h), C.byref(par), 0, 0, 1))
+    dev = torch.device("cuda", 0)
+    st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)  # noqa: E731
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    out = {"lib": os.path.basename(os.path.dirname(LIB_PATH)) + "/" + os.path.basename(LIB_PATH)}
+    for N in (65536, 16384):
+        H = N // 2
+        cnt = 512 if N == 65536 else 2048
+        src = torch.randint(0, 2**31 - 1, (2, cnt, H), dtype=torch.int32, device=dev)
+        dst = torch.zeros((cnt, N), dtype=torch.int64, device=dev)
+        back = torch.zeros((cnt, N), dtype=torch.int64, device=dev)
+
+        def timeit(fn, reps=10):
+            for _ in range(3):
+                fn(0)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(reps):
+                fn(i)
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+
+        ms_f = timeit(lambda i: check(lib.cuhe_ntt_ext_batch(h, p(dst), p(src[i % 2]), N, cnt, C.c_longlong(H), st())))
+        ms_i = timeit(lambda i: check(lib.cuhe_intt_batch(h, p(back), p(dst), N, cnt, st())))
+        out[f"fwd_{N}"] = {"ntt_per_s": cnt / ms_f * 1e3, "GBps": 10 * N * cnt / ms_f / 1e6, "ms": ms_f}
+        out[f"inv_{N}"] = {"ntt_per_s": cnt / ms_i * 1e3, "GBps": 16 * N * cnt / ms_i / 1e6, "ms": ms_i}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
