@@ -75,21 +75,25 @@ __global__ void __launch_bounds__(CUHE_P1V2_THREADS) ntt_pass1_v2_kernel(Pass1Ar
         dg_two = (dg_lo + 1) < a.digit_words;
         dg_mask = (1ull << a.digit_w) - 1;
     }
-#pragma unroll 1
-    for (int i = 0; i < 8; i++) {
-        uint64_t x[8];
+    // layer A, software pipelined: the loads of iteration i+1 are in flight while
+    // iteration i is transformed (ncu: long_scoreboard was the top stall without this)
+    constexpr int NIN = EXT ? 4 : 8;
+    constexpr int NIN2 = (MODE == IN_U64_REV_MUL) ? 8 : 1;
+    uint64_t nx[NIN], ny[NIN2];
+    auto fetch = [&](int i, uint64_t (&v)[NIN], uint64_t (&v2)[NIN2]) {
         if constexpr (MODE == IN_EXT_U32) {
-            const uint32_t* s = (const uint32_t*)a.src + (long long)t * a.src_stride + j2;
+            const uint32_t* s = (const uint32_t*)a.src + (long long)t * a.src_stride + j2 + i * n2;
 #pragma unroll
-            for (int k = 0; k < 4; k++) x[k] = __ldg(s + (long long)(i + 8 * k) * n2);
+            for (int k = 0; k < 4; k++) v[k] = __ldg(s + k * 8 * n2);
         } else if constexpr (MODE == IN_DIGIT) {
-            const uint32_t* s = (const uint32_t*)a.src;
+            const uint32_t* s = (const uint32_t*)a.src + (long long)(i * n2 + j2) * a.digit_words + dg_lo;
+            const long long step = (long long)8 * n2 * a.digit_words;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const uint32_t* c = s + ((long long)(i + 8 * k) * n2 + j2) * a.digit_words + dg_lo;
-                uint64_t v = __ldg(c);
-                if (dg_two) v |= (uint64_t)__ldg(c + 1) << 32;
-                x[k] = (v >> dg_sh) & dg_mask;
+                const uint32_t* c = s + k * step;
+                uint64_t w = __ldg(c);
+                if (dg_two) w |= (uint64_t)__ldg(c + 1) << 32;
+                v[k] = (w >> dg_sh) & dg_mask;
             }
         } else {
             const uint64_t* s = (const uint64_t*)a.src + (long long)t * a.src_stride;
@@ -97,11 +101,21 @@ __global__ void __launch_bounds__(CUHE_P1V2_THREADS) ntt_pass1_v2_kernel(Pass1Ar
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 const int e = (N - ((i + 8 * k) * n2 + j2)) & (N - 1);
-                uint64_t v = __ldg(s + e);
-                if constexpr (MODE == IN_U64_REV_MUL) v = mul_modP(v, __ldg(s2 + e));
-                x[k] = v;
+                v[k] = __ldg(s + e);
+                if constexpr (MODE == IN_U64_REV_MUL) v2[k] = __ldg(s2 + e);   // multiplied when consumed
             }
         }
+    };
+    fetch(0, nx, ny);
+#pragma unroll 1
+    for (int i = 0; i < 8; i++) {
+        uint64_t x[8];
+#pragma unroll
+        for (int k = 0; k < NIN; k++) {
+            if constexpr (MODE == IN_U64_REV_MUL) x[k] = mul_modP(nx[k], ny[k]);   // fused ntt_mul (Base.cu:1036)
+            else x[k] = nx[k];
+        }
+        if (i < 7) fetch(i + 1, nx, ny);
         ntt_regs<8, EXT>(x);                         // over k -> a = bitrev3(r)
         twiddle8_dyn(x, i);                          // * 2^(3*i*a)
 #pragma unroll
@@ -111,15 +125,14 @@ __global__ void __launch_bounds__(CUHE_P1V2_THREADS) ntt_pass1_v2_kernel(Pass1Ar
     const uint64_t* tw = a.tw1 + j2;
 #pragma unroll 1
     for (int aa = 0; aa < 8; aa++) {
-        uint64_t x[8];
+        uint64_t x[8], w[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) w[r] = __ldg(tw + (aa + 8 * bitrev(r, 3)) * n2);   // in flight during the butterfly
 #pragma unroll
         for (int i = 0; i < 8; i++) x[i] = col[(aa * 8 + i) * T];
         ntt_regs<8, false>(x);                       // over i -> b = bitrev3(r)
 #pragma unroll
-        for (int r = 0; r < 8; r++) {
-            const int k1 = aa + 8 * bitrev(r, 3);
-            d[(long long)k1 * n2] = mul_modP(x[r], __ldg(tw + (long long)k1 * n2));
-        }
+        for (int r = 0; r < 8; r++) d[(aa + 8 * bitrev(r, 3)) * n2] = mul_modP(x[r], w[r]);
     }
 }
 
@@ -144,11 +157,18 @@ __global__ void __launch_bounds__(128) ntt_pass2_v2_kernel(Pass2Args a) {
         const int j2b = tid % R3, row = tid / R3;
         const uint64_t* s = a.scratch + (long long)t * N + (long long)(r0 + row) * N2 + j2b;
         uint64_t* col = sm + row * RS + j2b;
+        uint64_t nx[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) nx[k] = s[(8 * k) * R3];
 #pragma unroll 1
         for (int i = 0; i < 8; i++) {
             uint64_t x[8];
 #pragma unroll
-            for (int k = 0; k < 8; k++) x[k] = s[(i + 8 * k) * R3];
+            for (int k = 0; k < 8; k++) x[k] = nx[k];
+            if (i < 7) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) nx[k] = s[(i + 1 + 8 * k) * R3];
+            }
             ntt_regs<8, false>(x);
             twiddle8_dyn(x, i);
 #pragma unroll
