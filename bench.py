@@ -185,12 +185,10 @@ def run_ours(args):
     a_np, b_np = gen_raw(info, B, NBUF, 20260924)
     a_dev = torch.from_numpy(a_np.view(np.int32)).to(dev)
     b_dev = torch.from_numpy(b_np.view(np.int32)).to(dev)
+    from cuhe_b200 import sharded as sh
     crt_loc = torch.zeros((B, rows, H), dtype=torch.int32, device=dev)
-    crt_all = torch.zeros((B, L, H), dtype=torch.int32, device=dev)
-    gather = torch.zeros((world, B, rows, H), dtype=torch.int32, device=dev) if world > 1 else None
     raw_out = torch.zeros((B, H, W), dtype=torch.int32, device=dev)
-    Hs = H // world
-    raw_gather = torch.zeros((world, B, Hs, W), dtype=torch.int32, device=dev) if world > 1 else None
+    cb, ce = sh.coefficient_slice(H, rank, world)
     st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)  # noqa: E731
     p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
 
@@ -200,11 +198,9 @@ def run_ours(args):
         if world == 1:
             check(lib.cuhe_icrt_batch(h, p(raw_out), p(crt_loc), 0, 0, H, B, st()))
         else:
-            dist.all_gather_into_tensor(gather, crt_loc)                 # NCCL over NVLink
-            crt_all.view(B, rows, world, H).copy_(gather.permute(1, 2, 0, 3))   # prime l = r + world*i
-            check(lib.cuhe_icrt_batch(h, p(raw_out), p(crt_all), 0, rank * Hs, (rank + 1) * Hs, B, st()))
-            dist.all_gather_into_tensor(raw_gather, raw_out[:, rank * Hs:(rank + 1) * Hs].contiguous())
-            raw_out.view(B, world, Hs, W).copy_(raw_gather.permute(1, 0, 2, 3))
+            crt_all = sh.all_gather_residues(crt_loc, L, world)          # NCCL all-gather over NVLink
+            check(lib.cuhe_icrt_batch(h, p(raw_out), p(crt_all), 0, cb, ce, B, st()))
+            return sh.all_gather_raw(raw_out, rank, world)               # complete RAW on every rank
 
     def barrier():
         if world > 1:

@@ -1,0 +1,79 @@
+"""Residue-sharded multi-GPU plumbing (one process per GPU, torch.distributed).
+
+The reference has no collective (one OpenMP thread per GPU, whole
+ciphertexts per device).  Here the CRT-residue axis is sharded: rank r of G owns
+primes r, r+G, r+2G, ... (so every level stays balanced while modSwitch drops
+the last prime).  Collectives appear only where the algorithm exchanges data:
+
+  * all-gather of cRep before ICRT (cuhe/CuHE.cu:366-382 needs every residue),
+    ICRT split by coefficient range, all-gather of the RAW slices;
+  * broadcast of the dropped residue row in modSwitch (cuhe/Base.cu:1112-1138).
+
+The index arithmetic is pure torch (CPU or CUDA tensors) so it is tested on CPU
+with the gloo backend (tests/test_dist_cpu.py); the compute goes through the C ABI.
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def local_primes(L: int, rank: int, world: int) -> List[int]:
+    """Prime indices owned by `rank` at a level with L primes."""
+    return list(range(rank, L, world))
+
+
+def rows_of(L: int, rank: int, world: int) -> int:
+    return (L - rank + world - 1) // world if rank < L else 0
+
+
+def owner_of(prime: int, world: int) -> Tuple[int, int]:
+    """(rank, local row) holding prime index `prime`."""
+    return prime % world, prime // world
+
+
+def all_gather_residues(local: torch.Tensor, L: int, world: int, group=None) -> torch.Tensor:
+    """local: [batch][rows][H] (rows padded to ceil(L/world) on every rank)
+    -> [batch][L][H] in prime order on every rank."""
+    B, rows_pad, H = local.shape
+    if world == 1:
+        return local[:, :L]
+    gathered = torch.empty((world * B, rows_pad, H), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(gathered, local.contiguous(), group=group)    # rank-major concatenation
+    gathered = gathered.view(world, B, rows_pad, H)
+    # gathered[r, b, i, :] is prime r + world*i
+    full = gathered.permute(1, 2, 0, 3).reshape(B, rows_pad * world, H)
+    return full[:, :L].contiguous()
+
+
+def coefficient_slice(H: int, rank: int, world: int) -> Tuple[int, int]:
+    step = (H + world - 1) // world
+    return min(rank * step, H), min((rank + 1) * step, H)
+
+
+def all_gather_raw(raw: torch.Tensor, rank: int, world: int, group=None) -> torch.Tensor:
+    """raw: [batch][H][W] with only this rank's coefficient slice valid ->
+    complete RAW polynomials on every rank."""
+    if world == 1:
+        return raw
+    B, H, W = raw.shape
+    step = (H + world - 1) // world
+    assert step * world == H, "crtLen is a power of two; world must divide it"
+    b, e = coefficient_slice(H, rank, world)
+    mine = raw[:, b:e].contiguous()
+    gathered = torch.empty((world * B, step, W), dtype=raw.dtype, device=raw.device)
+    dist.all_gather_into_tensor(gathered, mine, group=group)
+    return gathered.view(world, B, step, W).permute(1, 0, 2, 3).reshape(B, H, W).contiguous()
+
+
+def broadcast_last_row(local: torch.Tensor, L: int, rank: int, world: int, group=None) -> torch.Tensor:
+    """local: [rows][H] residues of this rank at a level with L primes.  Returns
+    the row of prime L-1 on every rank (input of cuhe_mod_switch)."""
+    H = local.shape[-1]
+    owner, row = owner_of(L - 1, world)
+    buf = local[row].clone() if rank == owner else torch.empty(H, dtype=local.dtype, device=local.device)
+    if world > 1:
+        dist.broadcast(buf, src=owner, group=group)
+    return buf
