@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -74,6 +75,11 @@ struct cuhe_ctx {
     bool have_polymod = false;
     uint64_t *d_u_ntt = nullptr, *d_m_ntt = nullptr;
     uint32_t* d_m_crt = nullptr;
+    // fast reduction modulo Phi_m (needs Phi | x^m - 1): quotient through an Nq-point product,
+    // q*Phi through an Nr-point product; tables for the local rows of level 0
+    bool fast_reduce = false;
+    int Nq = 0, Nr = 0, k1 = 0;            // k1 = m - n quotient coefficients
+    uint64_t *d_tq = nullptr, *d_tr = nullptr;
     // relinearization keys: [rows(0)][numEvalKey][N]
     uint64_t* d_ek = nullptr;
     std::mutex mu;
@@ -151,6 +157,23 @@ static void fwd_ntt(cuhe_ctx* c, int N, uint64_t* dst, const uint32_t* src, long
     b.row_mod = row_mod > 0 ? row_mod : 1;
     CK(launch_pass2(pl.r3, mul_tab ? OUT_U64_MUL : OUT_U64, b, count, st));
 }
+// forward transform whose zero-padded input is gathered (and optionally folded mod x^m - 1):
+// x[j] = src[t*stride + base + dir*j] (+ src[.. + fold_m] mod p), j < len
+static void fwd_ntt_map(cuhe_ctx* c, int N, uint64_t* dst, const uint32_t* src, long long src_stride, int count,
+                        int len, int base, int dir, int fold_m, int fold_lim, const uint64_t* mul_tab, int row_mod,
+                        cudaStream_t st) {
+    const NttPlan& pl = get_plan(c, N);
+    Tmp scratch(c, (size_t)count * N * 8, st);
+    Pass1Args a{};
+    a.scratch = scratch.as<uint64_t>(); a.src = src; a.tw1 = pl.tw1; a.src_stride = src_stride; a.n2 = pl.n2;
+    a.map_len = len; a.map_base = base; a.map_dir = dir; a.fold_m = fold_m; a.fold_lim = fold_lim;
+    a.primes = c->d_primes; a.prime_base = c->rank; a.prime_step = c->world; a.row_mod = row_mod > 0 ? row_mod : 1;
+    CK(launch_pass1(IN_U32_MAP, a, count, st));
+    Pass2Args b{};
+    b.dst = dst; b.scratch = scratch.as<uint64_t>(); b.tw2 = pl.tw2; b.mul_tab = mul_tab; b.dst_stride = N;
+    b.row_mod = row_mod > 0 ? row_mod : 1;
+    CK(launch_pass2(pl.r3, mul_tab ? OUT_U64_MUL : OUT_U64, b, count, st));
+}
 // inverse transform + % p of `count` = k*rows transforms -> u32[count][N] (all outputs)
 static void inv_ntt_modp(cuhe_ctx* c, int N, uint32_t* dst, const uint64_t* src, const uint64_t* src2, int count,
                          int row_mod, cudaStream_t st) {
@@ -185,6 +208,47 @@ static void barrett_impl(cuhe_ctx* c, uint32_t* dst, const uint32_t* hold, int l
     dim3 grid((H + 255) / 256, cnt);
     barrett_finish_kernel<<<grid, 256, 0, st>>>(dst, hold, t.as<uint32_t>(), s.as<uint32_t>(), c->d_m_crt, c->pv(), rows,
                                                n, H, N);
+    count_launch();
+    CK(cudaGetLastError());
+}
+
+// out[i] = (f[i] + f[i+m]) - d[i]  (mod p) for i < n, 0 for n <= i < H          (fast reduction tail)
+__global__ void __launch_bounds__(256)
+fold_sub_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ f, const uint32_t* __restrict__ d, PrimeView pv,
+                int row_mod, int n, int m, int H, int N, int Nr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (i >= H) return;
+    uint32_t v = 0;
+    if (i < n) {
+        const uint32_t p = pv.p[pv.base + pv.step * (r % row_mod)];
+        v = f[(long long)r * N + i];
+        if (i + m < N) { v += f[(long long)r * N + i + m]; if (v >= p) v -= p; }
+        const uint32_t s = d[(long long)r * Nr + i];
+        if (v < s) v += p;
+        v -= s;
+    }
+    out[(long long)r * H + i] = v;
+}
+
+// (f mod Phi_m) for `batch` polynomials when Phi_m | x^m - 1.  Same canonical result as barrett_impl
+// (the quotient of the division is unique), 1.5 instead of 4 nttLen-sized transforms per residue:
+//   f' = f mod (x^m - 1)                                   (fused into the loads below)
+//   rev(q) = rev(top k1 coeffs of f') * rev(Phi)^-1 mod x^k1     Nq-point product, k1 = m - n
+//   out = f' - q*Phi  on coefficients [0,n)                Nr-point product (deg q*Phi = m-1 < Nr)
+static void reduce_fast_impl(cuhe_ctx* c, uint32_t* dst, const uint32_t* hold, int lvl, int batch, cudaStream_t st) {
+    const int N = c->par.nttLen, H = c->par.crtLen, n = c->par.modLen, m = c->par.mSize, rows = c->rows(lvl);
+    const int cnt = rows * batch, Nq = c->Nq, Nr = c->Nr, k1 = c->k1;
+    if (cnt == 0) return;
+    Tmp g(c, (size_t)cnt * std::max(Nq, Nr) * 8, st), qrev(c, (size_t)cnt * Nq * 4, st), d(c, (size_t)cnt * Nr * 4, st);
+    // a[j] = f'[m-1-j], j < k1 ; times NTT(rev(Phi)^-1)
+    fwd_ntt_map(c, Nq, g.as<uint64_t>(), hold, N, cnt, k1, m - 1, -1, m, N, c->d_tq, rows, st);
+    inv_ntt_modp(c, Nq, qrev.as<uint32_t>(), g.as<uint64_t>(), nullptr, cnt, rows, st);     // qrev[j] = q[k1-1-j]
+    // b[j] = q[j] = qrev[k1-1-j] ; times NTT(Phi)
+    fwd_ntt_map(c, Nr, g.as<uint64_t>(), qrev.as<uint32_t>(), Nq, cnt, k1, k1 - 1, -1, 0, 0, c->d_tr, rows, st);
+    inv_ntt_modp(c, Nr, d.as<uint32_t>(), g.as<uint64_t>(), nullptr, cnt, rows, st);         // d = q*Phi
+    dim3 grid((H + 255) / 256, cnt);
+    fold_sub_kernel<<<grid, 256, 0, st>>>(dst, hold, d.as<uint32_t>(), c->pv(), rows, n, m, H, N, Nr);
     count_launch();
     CK(cudaGetLastError());
 }
@@ -413,6 +477,7 @@ int cuhe_ctx_destroy(cuhe_ctx* c) {
         for (auto& d : c->icrt) { cudaFree(d.M); cudaFree(d.mi); cudaFree(d.bi); }
         cudaFree(c->d_primes); cudaFree(c->d_mus); cudaFree(c->d_pow32); cudaFree(c->d_invp);
         cudaFree(c->d_u_ntt); cudaFree(c->d_m_ntt); cudaFree(c->d_m_crt); cudaFree(c->d_ek);
+        cudaFree(c->d_tq); cudaFree(c->d_tr);
         if (c->pool) cudaMemPoolDestroy(c->pool);
         delete c;
     });
@@ -444,7 +509,9 @@ int cuhe_ctx_set_poly_modulus_host(cuhe_ctx* c, const int64_t* coeffs, int ncoef
         REQUIRE(coeffs[n] == 1, "polynomial modulus must be monic");
         DeviceGuard dg(c->device);
         std::vector<int64_t> phi(coeffs, coeffs + ncoeffs);
-        std::vector<int64_t> u = hm::barrett_u(phi);          // floor(x^(2n-1)/Phi), cuhe/Operations.cu:216-219
+        std::vector<int64_t> inv = hm::inverse_series_rev(phi);
+        std::vector<int64_t> u(n);                            // floor(x^(2n-1)/Phi), cuhe/Operations.cu:216-219
+        for (int j = 0; j < n; j++) u[j] = inv[n - 1 - j];
         const int rows = c->rows(0);
         cudaStream_t st = 0;
         if (c->d_u_ntt) { cudaFree(c->d_u_ntt); cudaFree(c->d_m_ntt); cudaFree(c->d_m_crt); c->d_u_ntt = nullptr; }
@@ -469,6 +536,48 @@ int cuhe_ctx_set_poly_modulus_host(cuhe_ctx* c, const int64_t* coeffs, int ncoef
             fwd_ntt(c, N, c->d_u_ntt, d_ucrt, H, rows, nullptr, 1, st);
             CK(cudaStreamSynchronize(st));
             cudaFree(d_co); cudaFree(d_ucrt);
+        }
+        // ---- fast reduction tables (only when Phi | x^m - 1, i.e. Phi is the m-th cyclotomic) ----
+        c->fast_reduce = false;
+        if (c->d_tq) { cudaFree(c->d_tq); cudaFree(c->d_tr); c->d_tq = c->d_tr = nullptr; }
+        const int m = c->par.mSize, k1 = m - n;
+        auto fit = [](int need_half, int need_full) {
+            for (int len : {16384, 32768, 65536}) if (len / 2 >= need_half && len >= need_full) return len;
+            return 0;
+        };
+        const int Nq = fit(k1, 2 * k1 - 1), Nr = fit(k1, m);
+        const char* force = getenv("CUHE_B200_LITERAL_BARRETT");
+        if (!(force && force[0] == '1') && k1 >= 1 && Nq && Nr && Nr <= N && m <= N && 2 * n - 2 < 2 * m &&
+            hm::divides_xm_minus_1(phi, m)) {
+            c->Nq = Nq; c->Nr = Nr; c->k1 = k1;
+            CK(cudaMalloc(&c->d_tq, std::max<size_t>(1, (size_t)rows * Nq * 8)));
+            CK(cudaMalloc(&c->d_tr, std::max<size_t>(1, (size_t)rows * Nr * 8)));
+            if (rows > 0) {
+                // Tq = NTT_Nq(first k1 terms of rev(Phi)^-1), residues taken on the device
+                long long* d_co = nullptr; uint32_t* d_crt = nullptr;
+                CK(cudaMalloc(&d_co, (size_t)k1 * 8));
+                CK(cudaMalloc(&d_crt, (size_t)rows * (Nq / 2) * 4));
+                CK(cudaMemcpy(d_co, inv.data(), (size_t)k1 * 8, cudaMemcpyHostToDevice));
+                dim3 grid((Nq / 2 + 255) / 256, rows);
+                small_poly_crt_kernel<<<grid, 256, 0, st>>>(d_crt, d_co, k1, c->pv(), Nq / 2);
+                CK(cudaGetLastError());
+                fwd_ntt(c, Nq, c->d_tq, d_crt, Nq / 2, rows, nullptr, 1, st);
+                CK(cudaStreamSynchronize(st));
+                cudaFree(d_co); cudaFree(d_crt);
+                // Tr = NTT_Nr(Phi) (n+1 coefficients can exceed Nr/2: full-length transform on the host)
+                std::vector<uint64_t> a(Nr);
+                for (int r = 0; r < rows; r++) {
+                    const int64_t p = c->primes[c->rank + c->world * r];
+                    for (int i = 0; i < Nr; i++) {
+                        int64_t v = i <= n ? phi[i] % p : 0;
+                        a[i] = (uint64_t)(v < 0 ? v + p : v);
+                    }
+                    hm::host_ntt(a);
+                    CK(cudaMemcpy(c->d_tr + (size_t)r * Nr, a.data(), (size_t)Nr * 8, cudaMemcpyHostToDevice));
+                }
+            }
+            get_plan(c, Nq); get_plan(c, Nr);
+            c->fast_reduce = true;
         }
         c->have_polymod = true;
     });
@@ -545,7 +654,8 @@ static void intt_mod_impl(cuhe_ctx* c, uint32_t* dst, const uint64_t* x, const u
     if (!c->have_polymod) throw StateError{"Barrett reduction needs cuhe_ctx_set_poly_modulus_host first"};
     Tmp hold(c, (size_t)rows * batch * N * 4, st);
     inv_ntt_modp(c, N, hold.as<uint32_t>(), x, y, rows * batch, rows, st);
-    barrett_impl(c, dst, hold.as<uint32_t>(), lvl, batch, st);
+    if (c->fast_reduce) reduce_fast_impl(c, dst, hold.as<uint32_t>(), lvl, batch, st);
+    else barrett_impl(c, dst, hold.as<uint32_t>(), lvl, batch, st);
 }
 // raw a,b u32[batch][H][W] (device) -> product residues u32[batch][rows][H]
 static void mul_crt_batch_impl(cuhe_ctx* c, uint32_t* dst, const uint32_t* a_raw, const uint32_t* b_raw, int lvl, int batch,

@@ -11,7 +11,10 @@ enum Pass1In {
     IN_EXT_U32 = 0,     // u32[N/2] zero-padded input                        (ntt_1_*_ext)
     IN_DIGIT = 1,       // w-bit window of multi-word raw coefficients        (ntt_1_*_ext_block)
     IN_U64_REV = 2,     // u64[N] read at (N-i) mod N: inverse DFT            (intt_1_*)
-    IN_U64_REV_MUL = 3  // same, input is the pointwise product a[i]*b[i]     (fused ntt_mul)
+    IN_U64_REV_MUL = 3, // same, input is the pointwise product a[i]*b[i]     (fused ntt_mul)
+    IN_U32_MAP = 4      // zero-padded u32 input gathered as x[j] = src[map_base + map_dir*j] for
+                        // j < map_len (0 beyond), optionally folded modulo x^m - 1:
+                        // + src[idx + fold_m] (mod p) when fold_m > 0 and idx + fold_m < fold_lim
 };
 struct Pass1Args {
     uint64_t* scratch;         // [count][N]
@@ -23,6 +26,10 @@ struct Pass1Args {
     int n2;                    // N / 64
     int digit_w, digit_words;  // IN_DIGIT: window bits, words per coefficient
     int digit_first;           // IN_DIGIT: transform t extracts window digit_first + t
+    // IN_U32_MAP
+    int map_len, map_base, map_dir, fold_m, fold_lim;
+    const uint32_t* primes;    // fold: p of transform t is primes[prime_base + prime_step*(t % row_mod)]
+    int prime_base, prime_step, row_mod;
 };
 enum Pass2Out {
     OUT_U64 = 0,       // natural-order u64[N]                                (ntt_3_*)

@@ -27,6 +27,43 @@ inline uint64_t powP(uint64_t b, uint64_t e) {
     return r;
 }
 
+// fast product (2^64 == 2^32-1, 2^96 == -1 mod P) for the init-time host transforms
+inline uint64_t mulP_fast(uint64_t a, uint64_t b) {
+    u128 t = (u128)a * b;
+    uint64_t lo = (uint64_t)t, hi = (uint64_t)(t >> 64);
+    uint64_t hh = hi >> 32, hl = hi & 0xFFFFFFFFULL;
+    uint64_t r = lo - hh;
+    if (lo < hh) r -= 0xFFFFFFFFULL;
+    uint64_t m = hl * 0xFFFFFFFFULL, s = r + m;
+    if (s < r) s += 0xFFFFFFFFULL;
+    return s >= P ? s - P : s;
+}
+inline uint64_t addP(uint64_t a, uint64_t b) { uint64_t s = a + b; if (s < a) s += 0xFFFFFFFFULL; return s >= P ? s - P : s; }
+inline uint64_t subP(uint64_t a, uint64_t b) { uint64_t d = a - b; if (a < b) d -= 0xFFFFFFFFULL; return d; }
+// in-place natural-order cyclic NTT of a.size() = N points with w = g^(65536/N) (init-time tables only)
+inline void host_ntt(std::vector<uint64_t>& a) {
+    const int N = (int)a.size();
+    std::vector<uint64_t> roots(N / 2);
+    const uint64_t w0 = powP(G, (uint64_t)(65536 / N));
+    roots[0] = 1;
+    for (int i = 1; i < N / 2; i++) roots[i] = mulP_fast(roots[i - 1], w0);
+    for (int i = 1, j = 0; i < N; i++) {
+        int bit = N >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) std::swap(a[i], a[j]);
+    }
+    for (int len = 2; len <= N; len <<= 1) {
+        const int half = len >> 1, step = N / len;
+        for (int s = 0; s < N; s += len)
+            for (int k = 0; k < half; k++) {
+                uint64_t u = a[s + k], v = mulP_fast(a[s + k + half], roots[k * step]);
+                a[s + k] = addP(u, v);
+                a[s + k + half] = subP(u, v);
+            }
+    }
+}
+
 // ---- small integers --------------------------------------------------------
 inline int num_bits(uint64_t x) { int b = 0; while (x) { b++; x >>= 1; } return b; }   // NTL NumBits
 inline uint64_t isqrt(uint64_t x) {                                                     // NTL SqrRoot
@@ -224,7 +261,16 @@ inline IcrtConst gen_icrt(const Params& q, const std::vector<uint32_t>& pr, cons
 
 // u = floor(x^(2n-1) / Phi) over Z for monic Phi of degree n (cuhe/Operations.cu:216-219).
 // Returned as n signed coefficients u_0..u_{n-1}.  Power-series inverse of the reversed Phi.
+// power series inverse of the reversed Phi, n terms: inv[0..n)
+inline std::vector<int64_t> inverse_series_rev(const std::vector<int64_t>& phi);
 inline std::vector<int64_t> barrett_u(const std::vector<int64_t>& phi) {
+    const int n = (int)phi.size() - 1;
+    std::vector<int64_t> inv = inverse_series_rev(phi);
+    std::vector<int64_t> u(n);
+    for (int j = 0; j < n; j++) u[j] = inv[n - 1 - j];
+    return u;
+}
+inline std::vector<int64_t> inverse_series_rev(const std::vector<int64_t>& phi) {
     const int n = (int)phi.size() - 1;
     if (n < 1 || phi[n] != 1) throw std::invalid_argument("polynomial modulus must be monic");
     std::vector<int64_t> rev(phi.rbegin(), phi.rend());       // rev[0] == 1
@@ -243,9 +289,23 @@ inline std::vector<int64_t> barrett_u(const std::vector<int64_t>& phi) {
             inv[idx] -= c * kv.second;
         }
     }
-    std::vector<int64_t> u(n);
-    for (int j = 0; j < n; j++) u[j] = inv[n - 1 - j];
-    return u;
+    return inv;
+}
+// does Phi divide x^m - 1 ?  (true for the m-th cyclotomic polynomial)
+inline bool divides_xm_minus_1(const std::vector<int64_t>& phi, int m) {
+    const int n = (int)phi.size() - 1;
+    if (m < n || phi[n] != 1) return false;
+    std::vector<int64_t> r(m + 1, 0);
+    r[m] = 1; r[0] = -1;
+    const int64_t lim = (int64_t)1 << 40;
+    for (int i = m; i >= n; i--) {
+        const int64_t c = r[i];
+        if (c == 0) continue;
+        if (c > lim || c < -lim) return false;
+        for (int k = 0; k <= n; k++) r[i - n + k] -= c * phi[k];
+    }
+    for (int i = 0; i < n; i++) if (r[i] != 0) return false;
+    return true;
 }
 
 }  // namespace hm

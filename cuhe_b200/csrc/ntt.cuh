@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(CUHE_P1_THREADS) ntt_pass1_kernel(Pass1Args a)
             x[j1] = v;
         }
     }
+    static_assert(MODE != IN_U32_MAP, "generation-1 pass 1 has no gather mode");
     ntt_regs<64, (MODE == IN_EXT_U32 || MODE == IN_DIGIT)>(x);
     uint64_t* d = a.scratch + (long long)t * N + j2;
     const uint64_t* tw = a.tw1 + j2;

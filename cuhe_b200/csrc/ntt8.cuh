@@ -58,7 +58,7 @@ __device__ __forceinline__ void twiddle8_dyn(uint64_t (&x)[8], int i) {
 template <int MODE>
 __global__ void __launch_bounds__(CUHE_P1V2_THREADS) ntt_pass1_v2_kernel(Pass1Args a) {
     constexpr int T = CUHE_P1V2_THREADS;
-    constexpr bool EXT = (MODE == IN_EXT_U32 || MODE == IN_DIGIT);
+    constexpr bool EXT = (MODE == IN_EXT_U32 || MODE == IN_DIGIT || MODE == IN_U32_MAP);
     extern __shared__ uint64_t S8[];                 // [64][T], column of thread tid at S8[.][tid]
     const int tid = threadIdx.x;
     const int j2 = blockIdx.x * T + tid;
@@ -75,6 +75,10 @@ __global__ void __launch_bounds__(CUHE_P1V2_THREADS) ntt_pass1_v2_kernel(Pass1Ar
         dg_two = (dg_lo + 1) < a.digit_words;
         dg_mask = (1ull << a.digit_w) - 1;
     }
+    uint32_t map_p = 0;
+    if constexpr (MODE == IN_U32_MAP) {
+        if (a.fold_m > 0) map_p = a.primes[a.prime_base + a.prime_step * (t % a.row_mod)];
+    }
     // layer A, software pipelined: the loads of iteration i+1 are in flight while
     // iteration i is transformed (ncu: long_scoreboard was the top stall without this)
     constexpr int NIN = EXT ? 4 : 8;
@@ -85,6 +89,22 @@ __global__ void __launch_bounds__(CUHE_P1V2_THREADS) ntt_pass1_v2_kernel(Pass1Ar
             const uint32_t* s = (const uint32_t*)a.src + (long long)t * a.src_stride + j2 + i * n2;
 #pragma unroll
             for (int k = 0; k < 4; k++) v[k] = __ldg(s + k * 8 * n2);
+        } else if constexpr (MODE == IN_U32_MAP) {
+            const uint32_t* s = (const uint32_t*)a.src + (long long)t * a.src_stride;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int j = (i + 8 * k) * n2 + j2;
+                uint32_t w = 0;
+                if (j < a.map_len) {
+                    const int idx = a.map_base + a.map_dir * j;
+                    w = __ldg(s + idx);
+                    if (a.fold_m > 0 && idx + a.fold_m < a.fold_lim) {
+                        w += __ldg(s + idx + a.fold_m);          // both < p < 2^26
+                        if (w >= map_p) w -= map_p;
+                    }
+                }
+                v[k] = w;
+            }
         } else if constexpr (MODE == IN_DIGIT) {
             const uint32_t* s = (const uint32_t*)a.src + (long long)(i * n2 + j2) * a.digit_words + dg_lo;
             const long long step = (long long)8 * n2 * a.digit_words;

@@ -41,6 +41,9 @@ cudaError_t launch_pass1(int mode, const Pass1Args& a, int count, cudaStream_t s
         case IN_DIGIT: return launch_p1<IN_DIGIT>(a, count, st);
         case IN_U64_REV: return launch_p1<IN_U64_REV>(a, count, st);
         case IN_U64_REV_MUL: return launch_p1<IN_U64_REV_MUL>(a, count, st);
+#ifndef CUHE_NTT_V1
+        case IN_U32_MAP: return launch_p1<IN_U32_MAP>(a, count, st);
+#endif
     }
     return cudaErrorInvalidValue;
 }
