@@ -82,6 +82,8 @@ struct cuhe_ctx {
     uint64_t *d_tq = nullptr, *d_tr = nullptr;
     // relinearization keys: [rows(0)][numEvalKey][N]
     uint64_t* d_ek = nullptr;
+    // internal streams/events of the pipelined host-buffer entry points
+    cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
     std::mutex mu;
 
     int L(int lvl) const { return par.numCrtPrimeAt(lvl); }
@@ -478,6 +480,7 @@ int cuhe_ctx_destroy(cuhe_ctx* c) {
         cudaFree(c->d_primes); cudaFree(c->d_mus); cudaFree(c->d_pow32); cudaFree(c->d_invp);
         cudaFree(c->d_u_ntt); cudaFree(c->d_m_ntt); cudaFree(c->d_m_crt); cudaFree(c->d_ek);
         cudaFree(c->d_tq); cudaFree(c->d_tr);
+        if (c->s_h2d) { cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_comp); cudaStreamDestroy(c->s_d2h); }
         if (c->pool) cudaMemPoolDestroy(c->pool);
         delete c;
     });
@@ -864,16 +867,48 @@ int cuhe_mul_raw_host_batch(cuhe_ctx* c, uint32_t* out_h, const uint32_t* a_h, c
         DeviceGuard dg(c->device);
         cudaStream_t st = (cudaStream_t)stream;
         const int L = c->L(lvl), W = c->par.wordsCoeffAt(lvl), H = c->par.crtLen;
-        const size_t raw_b = (size_t)batch * H * W * 4;
-        Tmp ra(c, raw_b, st), rb(c, raw_b, st), cc(c, (size_t)batch * L * H * 4, st);
-        CK(cudaMemcpyAsync(ra.p, a_h, raw_b, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(rb.p, b_h, raw_b, cudaMemcpyHostToDevice, st));
-        mul_crt_batch_impl(c, cc.as<uint32_t>(), ra.as<uint32_t>(), rb.as<uint32_t>(), lvl, batch, st);
-        // c2r + r2z (cuhe/CuHE.cu:366-382, 333-348)
-        CK(cudaMemsetAsync(ra.p, 0, raw_b, st));
-        do_icrt(c, ra.as<uint32_t>(), cc.as<uint32_t>(), lvl, 0, c->par.modLen, batch, st);
-        CK(cudaMemcpyAsync(out_h, ra.p, raw_b, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        const size_t poly_w = (size_t)H * W;                 // words per RAW polynomial
+        if (!c->s_h2d) {
+            CK(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+            CK(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
+            CK(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+        }
+        // three-stage pipeline over chunks of the batch: H2D | compute | D2H on separate streams, so
+        // PCIe transfers in both directions overlap the kernels (the reference's z2r/r2z are
+        // synchronous per polynomial, cuhe/CuHE.cu:317-348)
+        // chunks of 8 products keep every launch large enough to fill the GPU; smaller batches run as one chunk
+        const int chunk = batch >= 16 ? 8 : batch;
+        const int nchunk = (batch + chunk - 1) / chunk;
+        cudaEvent_t ready;
+        CK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+        CK(cudaEventRecord(ready, st));                      // order after the caller's stream
+        CK(cudaStreamWaitEvent(c->s_h2d, ready, 0));
+        CK(cudaStreamWaitEvent(c->s_comp, ready, 0));
+        Tmp ra(c, (size_t)batch * poly_w * 4, c->s_comp), rb(c, (size_t)batch * poly_w * 4, c->s_comp);
+        Tmp cc(c, (size_t)batch * L * H * 4, c->s_comp), ro(c, (size_t)batch * poly_w * 4, c->s_comp);
+        CK(cudaEventRecord(ready, c->s_comp));               // buffers exist
+        CK(cudaStreamWaitEvent(c->s_h2d, ready, 0));
+        CK(cudaMemsetAsync(ro.p, 0, (size_t)batch * poly_w * 4, c->s_comp));
+        std::vector<cudaEvent_t> ev(2 * nchunk);
+        for (auto& e : ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (int i = 0; i < nchunk; i++) {
+            const int b0 = i * chunk, nb = std::min(chunk, batch - b0);
+            const size_t off = (size_t)b0 * poly_w, bytes = (size_t)nb * poly_w * 4;
+            CK(cudaMemcpyAsync(ra.as<uint32_t>() + off, a_h + off, bytes, cudaMemcpyHostToDevice, c->s_h2d));
+            CK(cudaMemcpyAsync(rb.as<uint32_t>() + off, b_h + off, bytes, cudaMemcpyHostToDevice, c->s_h2d));
+            CK(cudaEventRecord(ev[2 * i], c->s_h2d));
+            CK(cudaStreamWaitEvent(c->s_comp, ev[2 * i], 0));
+            uint32_t* cci = cc.as<uint32_t>() + (size_t)b0 * L * H;
+            mul_crt_batch_impl(c, cci, ra.as<uint32_t>() + off, rb.as<uint32_t>() + off, lvl, nb, c->s_comp);
+            do_icrt(c, ro.as<uint32_t>() + off, cci, lvl, 0, c->par.modLen, nb, c->s_comp);   // c2r (cuhe/CuHE.cu:366-382)
+            CK(cudaEventRecord(ev[2 * i + 1], c->s_comp));
+            CK(cudaStreamWaitEvent(c->s_d2h, ev[2 * i + 1], 0));
+            CK(cudaMemcpyAsync(out_h + off, ro.as<uint32_t>() + off, bytes, cudaMemcpyDeviceToHost, c->s_d2h));
+        }
+        CK(cudaStreamSynchronize(c->s_d2h));
+        CK(cudaStreamSynchronize(c->s_comp));
+        for (auto& e : ev) cudaEventDestroy(e);
+        cudaEventDestroy(ready);
     });
 }
 

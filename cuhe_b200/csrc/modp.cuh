@@ -31,18 +31,22 @@ __device__ __forceinline__ uint64_t canon(uint64_t x) {
         : "=r"(m) : "r"((uint32_t)x), "r"((uint32_t)(x >> 32)));
     return x + (uint64_t)m;
 }
+// d - m (mod 2^64) for a mask m in {0, 2^32-1}.  (Measured alternative: d + m*(2^32-1) - (m<<32)
+// moves this correction to the FMA pipe -- ALU-pipe instructions of a 64-point transform drop
+// 3275 -> 2335 -- but the batched 64K transform got 8 % slower on B200, so the plain form stays.)
+__device__ __forceinline__ uint64_t sub_mask(uint64_t d, uint32_t m) { return d - (uint64_t)m; }
 // a - b corrected once by +P: exact whenever b <= P (a arbitrary); canonical if both are
 __device__ __forceinline__ uint64_t sub_fix(uint64_t a, uint64_t b) {
     uint64_t d; uint32_t m;
     asm("{\n\tsub.cc.u64 %0, %2, %3;\n\tsubc.u32 %1, 0, 0;\n\t}" : "=l"(d), "=r"(m) : "l"(a), "l"(b));
-    return d - (uint64_t)m;
+    return sub_mask(d, m);
 }
 // (a + m) mod P in [0,P), given a + m < 2P and me = m + eps (no 64-bit overflow in me):
 // a + m >= P  <=>  a + me carries; then the low 64 bits are a + m - P, else subtract eps again.
 __device__ __forceinline__ uint64_t add_reduce(uint64_t a, uint64_t me) {
     uint64_t z; uint32_t k;
     asm("{\n\tadd.cc.u64 %0, %2, %3;\n\taddc.u32 %1, 0xffffffff, 0;\n\t}" : "=l"(z), "=r"(k) : "l"(a), "l"(me));
-    return z - (uint64_t)k;           // k = 0 on carry, 0xffffffff otherwise
+    return sub_mask(z, k);            // k = 0 on carry, 0xffffffff otherwise
 }
 // (a - b) mod P                                              (ModP.h:240-247)
 __device__ __forceinline__ uint64_t sub_modP(uint64_t a, uint64_t b) { return sub_fix(a, b); }
