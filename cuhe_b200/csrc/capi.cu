@@ -52,7 +52,12 @@ struct NttPlan {
     uint64_t* tw2 = nullptr;    // [64][r3]  w^(64*k2a*j2b)
 };
 
-struct IcrtDev { uint32_t *M = nullptr, *mi = nullptr, *bi = nullptr; int L = 0, W = 0, Wp = 0; };
+struct IcrtDev {
+    uint32_t *M = nullptr, *mi = nullptr, *bi = nullptr;
+    int L = 0, W = 0, Wp = 0;
+    double m_top = 0.0;        // M / 2^(32(W-2)): quotient estimate of icrt_kernel_v2
+    bool truncated = false;    // some M_l lost bits in the reference's BytesFromZZ: use the literal kernel
+};
 
 }  // namespace cuhe_b200
 
@@ -298,8 +303,29 @@ static void launch_icrt(uint32_t* dst, const uint32_t* src, cuhe_ctx* c, const I
                         cudaStream_t st) {
     const int cnt = e - b;
     dim3 grid((cnt + 127) / 128, batch);
-    icrt_kernel<WMAX><<<grid, 128, 0, st>>>(dst, src, c->d_primes, c->d_mus, ic.M, ic.mi, ic.bi, ic.L, ic.W, ic.Wp, b, e,
-                                            c->par.crtLen);
+    if (ic.truncated) {
+        icrt_kernel<WMAX><<<grid, 128, 0, st>>>(dst, src, c->d_primes, c->d_mus, ic.M, ic.mi, ic.bi, ic.L, ic.W, ic.Wp, b,
+                                                e, c->par.crtLen);
+    } else {
+        const size_t smem = ((size_t)ic.L * ic.Wp + ic.W) * 4;
+        icrt_kernel_v2<WMAX><<<grid, 128, smem, st>>>(dst, src, c->d_primes, c->d_mus, ic.M, ic.mi, ic.bi, ic.m_top, ic.L,
+                                                      ic.W, ic.Wp, b, e, c->par.crtLen);
+    }
+    count_launch();
+}
+template <int WMAX>
+static void launch_crt(cuhe_ctx* c, uint32_t* dst, const uint32_t* raw, int rows, int W, int batch, cudaStream_t st) {
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !done[dev]) {
+        CK(cudaFuncSetAttribute(crt_kernel_v2<WMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        done[dev] = true;
+    }
+    const int H = c->par.crtLen;
+    const size_t smem = ((size_t)rows * W + (size_t)128 * (W | 1)) * 4;
+    dim3 grid((H + 127) / 128, batch);
+    crt_kernel_v2<WMAX><<<grid, 128, smem, st>>>(dst, raw, c->pv(), rows, c->d_pow32, c->pow_stride, W, c->par.modLen, H);
     count_launch();
 }
 // ICRT of `batch` polynomials: crt_all u32[batch][L][H] -> raw u32[batch][H][W], coefficients [b,e)
@@ -320,10 +346,13 @@ static void do_icrt(cuhe_ctx* c, uint32_t* raw_out, const uint32_t* crt_all, int
 static void do_crt(cuhe_ctx* c, uint32_t* dst, const uint32_t* raw, int lvl, int batch, cudaStream_t st) {
     const int rows = c->rows(lvl), W = c->par.wordsCoeffAt(lvl), H = c->par.crtLen;
     if (rows == 0 || batch <= 0) return;
-    const size_t smem = (size_t)kCrtThreads * (W | 1) * 4;
-    dim3 grid((H + kCrtThreads - 1) / kCrtThreads, batch);
-    crt_kernel<<<grid, kCrtThreads, smem, st>>>(dst, raw, c->pv(), rows, c->d_pow32, c->pow_stride, W, c->par.modLen, H);
-    count_launch();
+    (void)H;
+    if (W <= 8) launch_crt<8>(c, dst, raw, rows, W, batch, st);
+    else if (W <= 20) launch_crt<20>(c, dst, raw, rows, W, batch, st);
+    else if (W <= 36) launch_crt<36>(c, dst, raw, rows, W, batch, st);
+    else if (W <= 52) launch_crt<52>(c, dst, raw, rows, W, batch, st);
+    else if (W <= 104) launch_crt<104>(c, dst, raw, rows, W, batch, st);
+    else throw ArgError{"coefficient modulus wider than 104 words"};
     CK(cudaGetLastError());
 }
 
@@ -459,7 +488,9 @@ int cuhe_ctx_create(cuhe_ctx** out, const cuhe_params* p, int device, int shard_
         for (int lvl = 0; lvl < c->par.depth; lvl++) {
             hm::IcrtConst ic = hm::gen_icrt(c->par, c->primes, c->moduli, lvl);
             IcrtDev d;
-            d.L = ic.L; d.W = ic.W; d.Wp = ic.Wp;
+            d.L = ic.L; d.W = ic.W; d.Wp = ic.Wp; d.truncated = ic.truncated;
+            for (int k = std::max(0, ic.W - 3); k < ic.W; k++)      // M / 2^(32(W-2)) from its top three words
+                d.m_top += (double)ic.M[k] * __builtin_ldexp(1.0, 32 * (k - (ic.W - 2)));
             d.M = upload(ic.M); d.mi = upload(ic.mi); d.bi = upload(ic.bi);
             c->icrt[lvl] = d;
         }

@@ -127,6 +127,155 @@ icrt_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, const 
 }
 
 // ---------------------------------------------------------------------------
+// CRT, generation 2: the W words of a coefficient live in registers (template
+// bucket WMAX), the table 2^(32k) mod p_l is staged in shared memory and read by
+// broadcast, so one IMAD.WIDE per (word, prime) remains (the first version issued
+// two loads per multiply-add and was LSU-bound).  Same result as crt_kernel.
+// ---------------------------------------------------------------------------
+template <int WMAX>
+__global__ void __launch_bounds__(128)
+crt_kernel_v2(uint32_t* __restrict__ dst, const uint32_t* __restrict__ raw, PrimeView pv, int rows,
+              const uint32_t* __restrict__ pow32, int pow_stride, int W, int n, int H) {
+    extern __shared__ uint32_t sh[];          // [rows][W] powers, then [128][W|1] staging
+    uint32_t* spw = sh;
+    uint32_t* sw = sh + rows * W;
+    const int ws = W | 1;
+    const int i0 = blockIdx.x * 128;
+    const int cnt = min(128, H - i0);
+    raw += (long long)blockIdx.y * H * W;
+    dst += (long long)blockIdx.y * rows * H;
+    for (int e = threadIdx.x; e < rows * W; e += 128) {
+        const int r = e / W, k = e - r * W;
+        spw[e] = pow32[(long long)prime_index(pv, r) * pow_stride + k];
+    }
+    for (int e = threadIdx.x; e < cnt * W; e += 128) {
+        const int c = e / W, k = e - c * W;
+        sw[c * ws + k] = raw[(long long)i0 * W + e];
+    }
+    __syncthreads();
+    const int i = i0 + threadIdx.x;
+    if (i >= n) {
+        if (i < H) for (int r = 0; r < rows; r++) dst[(long long)r * H + i] = 0;
+        return;
+    }
+    uint32_t c[WMAX];
+#pragma unroll
+    for (int k = 0; k < WMAX; k++) c[k] = k < W ? sw[threadIdx.x * ws + k] : 0u;
+    for (int r = 0; r < rows; r++) {
+        const int l = prime_index(pv, r);
+        const uint32_t* pw = spw + r * W;
+        uint64_t acc = 0, acc_hi = 0;         // p < 2^26: 16 products stay below 2^62
+#pragma unroll
+        for (int k = 0; k < WMAX; k++) {
+            if (k < W) {
+                acc += (uint64_t)c[k] * pw[k];
+                if ((k & 15) == 15) { acc_hi += acc >> 32; acc &= 0xFFFFFFFFull; }
+            }
+        }
+        const uint32_t p = pv.p[l];
+        const uint64_t mu = pv.mu[l];
+        const uint64_t t = mod_u64_u32(acc_hi, p, mu);
+        const uint32_t two32 = W > 1 ? pw[1] : (uint32_t)((1ull << 32) % p);
+        dst[(long long)r * H + i] = mod_u64_u32(t * two32 + mod_u64_u32(acc, p, mu), p, mu);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// ICRT, generation 2.  When no M_l was byte-truncated (checked on the host; the
+// reference would silently drop bits, cuhe/Operations.cu:127-128) the reference's
+// "add one term, subtract M once if >= M" loop (cuhe/Base.cu:880-924) returns
+// exactly (sum_l tt_l*M_l) mod M, so the sum is accumulated without per-term
+// compares and reduced once: quotient estimate from the top three words in
+// double precision, one multiply-subtract, at most three conditional subtracts.
+// M_l and M are staged in shared memory.
+// ---------------------------------------------------------------------------
+template <int WMAX>
+__global__ void __launch_bounds__(128)
+icrt_kernel_v2(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, const uint32_t* __restrict__ primes,
+               const uint64_t* __restrict__ mus, const uint32_t* __restrict__ M, const uint32_t* __restrict__ mi,
+               const uint32_t* __restrict__ bi, double m_top, int L, int W, int Wp, int i_begin, int i_end, int H) {
+    extern __shared__ uint32_t sh[];          // [L][Wp] M_l, [W] M
+    uint32_t* smi = sh;
+    uint32_t* sM = sh + L * Wp;
+    for (int e = threadIdx.x; e < L * Wp; e += 128) smi[e] = mi[e];
+    for (int e = threadIdx.x; e < W; e += 128) sM[e] = M[e];
+    __syncthreads();
+    const int idx = i_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= i_end) return;
+    src += (long long)blockIdx.y * L * H;
+    dst += (long long)blockIdx.y * H * W;
+    uint32_t sum[WMAX + 1];
+#pragma unroll
+    for (int k = 0; k <= WMAX; k++) sum[k] = 0;
+    for (int l = 0; l < L; l++) {
+        const uint32_t p = primes[l];
+        const uint64_t mu = mus[l];
+        const uint64_t tar = mod_u64_u32(src[(long long)l * H + idx], p, mu);
+        const uint32_t tt = mod_u64_u32(tar * bi[l], p, mu);
+        const uint32_t* m = smi + l * Wp;
+        uint64_t carry = 0;
+#pragma unroll
+        for (int k = 0; k <= WMAX; k++) {
+            if (k <= W) {
+                uint64_t t = (uint64_t)sum[k] + carry;
+                if (k < Wp) t += (uint64_t)tt * m[k];
+                sum[k] = (uint32_t)t;
+                carry = t >> 32;
+            }
+        }
+    }
+    // S = sum < L*M.  Quotient estimate from the top three words (scaled by 2^(-32(W-2)) like m_top).
+    double sd = 0.0;
+#pragma unroll
+    for (int k = 0; k <= WMAX; k++) {
+        if (k == W) sd += (double)sum[k] * 18446744073709551616.0;
+        if (k == W - 1) sd += (double)sum[k] * 4294967296.0;
+        if (k == W - 2) sd += (double)sum[k];
+    }
+    int cq = (int)(sd / m_top) - 1;
+    if (cq < 0) cq = 0;
+    {   // S -= cq * M
+        uint64_t borrow = 0;
+        const uint32_t q = (uint32_t)cq;
+#pragma unroll
+        for (int k = 0; k <= WMAX; k++) {
+            if (k <= W) {
+                const uint64_t sub = (k < W ? (uint64_t)q * sM[k] : 0ull) + borrow;
+                const uint64_t lo = sub & 0xFFFFFFFFull;
+                const uint64_t t = (uint64_t)sum[k] - lo;
+                sum[k] = (uint32_t)t;
+                borrow = (sub >> 32) + ((t >> 63) & 1);
+            }
+        }
+    }
+#pragma unroll 1
+    for (int it = 0; it < 4; it++) {          // S in [0, 3M) here; bring it below M
+        bool ge = true, decided = false;
+#pragma unroll
+        for (int k = WMAX; k >= 0; k--) {
+            if (k <= W && !decided) {
+                const uint32_t mk = (k < W) ? sM[k] : 0u;
+                if (sum[k] != mk) { ge = sum[k] > mk; decided = true; }
+            }
+        }
+        if (!ge) break;
+        uint32_t borrow = 0;
+#pragma unroll
+        for (int k = 0; k <= WMAX; k++) {
+            if (k <= W) {
+                const uint32_t mk = (k < W) ? sM[k] : 0u;
+                const uint64_t t = (uint64_t)sum[k] - mk - borrow;
+                sum[k] = (uint32_t)t;
+                borrow = (uint32_t)(t >> 63);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < WMAX; k++)
+        if (k < W) dst[(long long)idx * W + k] = sum[k];
+}
+
+// ---------------------------------------------------------------------------
 // modulus switching                                        (cuhe/Base.cu:1112-1138)
 // d = c_last (+- ep*p_last to clear the message parity, signed 32-bit exactly
 // as the reference's `int dirty`), then c_j <- (c_j - d) * p_last^-1 mod p_j.
