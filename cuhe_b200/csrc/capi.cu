@@ -323,7 +323,7 @@ static void launch_crt(cuhe_ctx* c, uint32_t* dst, const uint32_t* raw, int rows
         done[dev] = true;
     }
     const int H = c->par.crtLen;
-    const size_t smem = ((size_t)rows * W + (size_t)128 * (W | 1)) * 4;
+    const size_t smem = ((size_t)rows * ((W + 3) & ~3) + (size_t)128 * (W | 1)) * 4;
     dim3 grid((H + 127) / 128, batch);
     crt_kernel_v2<WMAX><<<grid, 128, smem, st>>>(dst, raw, c->pv(), rows, c->d_pow32, c->pow_stride, W, c->par.modLen, H);
     count_launch();

@@ -136,17 +136,18 @@ template <int WMAX>
 __global__ void __launch_bounds__(128)
 crt_kernel_v2(uint32_t* __restrict__ dst, const uint32_t* __restrict__ raw, PrimeView pv, int rows,
               const uint32_t* __restrict__ pow32, int pow_stride, int W, int n, int H) {
-    extern __shared__ uint32_t sh[];          // [rows][W] powers, then [128][W|1] staging
+    extern __shared__ uint32_t sh[];          // [rows][W4] powers (rows padded to 4 words), then [128][W|1] staging
+    const int W4 = (W + 3) & ~3;
     uint32_t* spw = sh;
-    uint32_t* sw = sh + rows * W;
+    uint32_t* sw = sh + rows * W4;
     const int ws = W | 1;
     const int i0 = blockIdx.x * 128;
     const int cnt = min(128, H - i0);
     raw += (long long)blockIdx.y * H * W;
     dst += (long long)blockIdx.y * rows * H;
-    for (int e = threadIdx.x; e < rows * W; e += 128) {
-        const int r = e / W, k = e - r * W;
-        spw[e] = pow32[(long long)prime_index(pv, r) * pow_stride + k];
+    for (int e = threadIdx.x; e < rows * W4; e += 128) {
+        const int r = e / W4, k = e - r * W4;
+        spw[e] = k < W ? pow32[(long long)prime_index(pv, r) * pow_stride + k] : 0u;
     }
     for (int e = threadIdx.x; e < cnt * W; e += 128) {
         const int c = e / W, k = e - c * W;
@@ -163,13 +164,17 @@ crt_kernel_v2(uint32_t* __restrict__ dst, const uint32_t* __restrict__ raw, Prim
     for (int k = 0; k < WMAX; k++) c[k] = k < W ? sw[threadIdx.x * ws + k] : 0u;
     for (int r = 0; r < rows; r++) {
         const int l = prime_index(pv, r);
-        const uint32_t* pw = spw + r * W;
+        const uint32_t* pw = spw + r * W4;
         uint64_t acc = 0, acc_hi = 0;         // p < 2^26: 16 products stay below 2^62
 #pragma unroll
-        for (int k = 0; k < WMAX; k++) {
+        for (int k = 0; k < WMAX; k += 4) {   // one 128-bit broadcast load feeds four multiply-adds
             if (k < W) {
-                acc += (uint64_t)c[k] * pw[k];
-                if ((k & 15) == 15) { acc_hi += acc >> 32; acc &= 0xFFFFFFFFull; }
+                const uint4 q = *reinterpret_cast<const uint4*>(pw + k);     // words >= W are zero (c[] too)
+                acc += (uint64_t)c[k] * q.x;
+                if (k + 1 < WMAX) acc += (uint64_t)c[k + 1 < WMAX ? k + 1 : 0] * q.y;
+                if (k + 2 < WMAX) acc += (uint64_t)c[k + 2 < WMAX ? k + 2 : 0] * q.z;
+                if (k + 3 < WMAX) acc += (uint64_t)c[k + 3 < WMAX ? k + 3 : 0] * q.w;
+                if ((k & 15) == 12) { acc_hi += acc >> 32; acc &= 0xFFFFFFFFull; }
             }
         }
         const uint32_t p = pv.p[l];
