@@ -74,3 +74,33 @@ def test_no_oracle_in_product():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "coracle" not in src, f
+
+
+def _build_c_client():
+    import subprocess
+    out = os.path.join(ROOT, "tests", "_abi_client")
+    libdir = os.path.join(ROOT, "cuhe_b200")
+    subprocess.check_call(["gcc", "-O1", "-o", out, os.path.join(ROOT, "tests", "abi_client.c"),
+                           "-I", os.path.join(ROOT, "include"), "-I", "/usr/local/cuda/include",
+                           "-L", libdir, "-lcuhe_b200", "-L", "/usr/local/cuda/lib64", "-lcudart",
+                           f"-Wl,-rpath,{libdir}", "-Wl,-rpath,/usr/local/cuda/lib64"])
+    return out
+
+
+def test_plain_c_client_host_mode(lib):
+    """The boundary is a C ABI: a C program includes the header, links the .so and
+    derives the reference's parameters without C++/Python/GPU."""
+    import subprocess
+    exe = _build_c_client()
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "params 8190 16384 7 141 5" in r.stdout and "host ok" in r.stdout
+
+
+@pytest.mark.gpu
+def test_plain_c_client_gpu_mode(lib):
+    import subprocess
+    exe = _build_c_client()
+    r = subprocess.run([exe, "gpu"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "gpu ok" in r.stdout
