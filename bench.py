@@ -43,6 +43,16 @@ def peaks():
         return {"hbm_gbs": 6650.0}, "fallback"
 
 
+def ntt_traffic(batch):
+    """dram__bytes_read+write of the two NTT pass kernels for one launch pair at this batch, from the
+    committed ncu --set full capture (profiles/ntt_traffic.json); None if it was taken at another batch."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ntt_traffic.json")))
+        return t["dram_bytes_per_launch_pair"] if t["batch"] == batch else None
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region."""
 
@@ -275,7 +285,7 @@ def run_ours(args):
         ntt_rate = cnt / (kms * 1e-3)
         roof = {"kernel": "ntt_pass1_v2_kernel<EXT_U32> + ntt_pass2_v2_kernel<16,U64> (one batched forward 64K NTT)",
                 "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-                "peak_source": pk_src + " (burst copy bandwidth)", "traffic": None,
+                "peak_source": pk_src + " (burst copy bandwidth)", "traffic": ntt_traffic(cnt),
                 "algorithmic_bytes_per_launch": NTT_BYTES_64K * cnt, "launch_ms": kms, "batch": cnt,
                 "note": "INT32-ALU bound (SURVEY F9): see DESIGN.md for the instruction-issue roofline"}
         del src, dst

@@ -353,12 +353,9 @@ class CuPolynomial:
         self.nRepCreate(st)
         lib = load_library()
         with torch.cuda.device(self.device_):
-            if self.logq_ > param.logCrtPrime:
-                check(lib.cuhe_ntt(ctx(self.device_), _ptr(self.nRep_), _ptr(self.cRep_), self._lvl(),
-                                   _stream_ptr(st, self.device_)))
-            else:   # plaintext: a single residue, not tied to a level
-                check(lib.cuhe_ntt_ext_batch(ctx(self.device_), _ptr(self.nRep_), _ptr(self.cRep_), param.nttLen, 1,
-                                             param.crtLen, _stream_ptr(st, self.device_)))
+            # a plaintext (logq <= logCrtPrime) is level -1: one residue (cuhe/Parameters.cu:107-109)
+            check(lib.cuhe_ntt(ctx(self.device_), _ptr(self.nRep_), _ptr(self.cRep_), self._lvl(),
+                               _stream_ptr(st, self.device_)))
         self.cRepFree()
         self.domain_ = 3
 

@@ -406,6 +406,12 @@ static void check_lvl(const cuhe_ctx* c, int lvl) {
     REQUIRE(c != nullptr, "null context");
     REQUIRE(lvl >= 0 && lvl < c->par.depth, "level out of range");
 }
+// transforms also accept lvl == -1: a plaintext (CuPtxt) is one residue, taken mod the first CRT prime
+// like the reference's _numCrtPrime(-1) == 1 / crtidx 0 (cuhe/Parameters.cu:107-109, cuhe/Operations.cu:420-427)
+static void check_lvl_or_ptxt(const cuhe_ctx* c, int lvl) {
+    REQUIRE(c != nullptr, "null context");
+    REQUIRE(lvl >= -1 && lvl < c->par.depth, "level out of range");
+}
 }  // namespace cuhe_b200
 
 extern "C" {
@@ -646,7 +652,7 @@ int cuhe_icrt(cuhe_ctx* c, uint32_t* raw_out, const uint32_t* crt_all, int lvl, 
 
 int cuhe_ntt(cuhe_ctx* c, uint64_t* dst, const uint32_t* src, int lvl, cuhe_stream stream) {
     return guarded([&] {
-        check_lvl(c, lvl); REQUIRE(dst && src, "null pointer");
+        check_lvl_or_ptxt(c, lvl); REQUIRE(dst && src, "null pointer");
         DeviceGuard dg(c->device);
         fwd_ntt(c, c->par.nttLen, dst, src, c->par.crtLen, c->rows(lvl), nullptr, 1, (cudaStream_t)stream);
     });
@@ -661,7 +667,7 @@ int cuhe_intt_double_deg(cuhe_ctx* c, uint32_t* dst, const uint64_t* src, int lv
 }
 int cuhe_intt(cuhe_ctx* c, uint32_t* dst, const uint64_t* src, int lvl, cuhe_stream stream) {
     return guarded([&] {
-        check_lvl(c, lvl); REQUIRE(dst && src, "null pointer");
+        check_lvl_or_ptxt(c, lvl); REQUIRE(dst && src, "null pointer");
         DeviceGuard dg(c->device);
         const int rows = c->rows(lvl), N = c->par.nttLen, H = c->par.crtLen;
         if (rows == 0) return;

@@ -100,9 +100,11 @@ int cuhe_crt(cuhe_ctx* ctx, uint32_t* dst, const uint32_t* raw, int lvl, cuhe_st
 int cuhe_icrt(cuhe_ctx* ctx, uint32_t* raw_out, const uint32_t* crt_all, int lvl, int coef_begin, int coef_end,
               cuhe_stream stream);
 /* ntt(): cuhe/Operations.cu:394-398 (kernels cuhe/Base.cu:309-437,492-608,659-785).
- * src u32[rows][crtLen] -> dst u64[rows][nttLen] */
+ * src u32[rows][crtLen] -> dst u64[rows][nttLen].  lvl == -1: a plaintext, one residue
+ * (GlobalParameters::_numCrtPrime(-1) == 1, cuhe/Parameters.cu:107-109) */
 int cuhe_ntt(cuhe_ctx* ctx, uint64_t* dst, const uint32_t* src, int lvl, cuhe_stream stream);
-/* intt(): cuhe/Operations.cu:420-427.  src u64[rows][nttLen] -> dst u32[rows][crtLen] (low half, % p) */
+/* intt(): cuhe/Operations.cu:420-427.  src u64[rows][nttLen] -> dst u32[rows][crtLen] (low half, % p).
+ * lvl == -1: a plaintext, reduced modulo the first CRT prime as the reference does (crtidx 0) */
 int cuhe_intt(cuhe_ctx* ctx, uint32_t* dst, const uint64_t* src, int lvl, cuhe_stream stream);
 /* inttDoubleDeg(): cuhe/Operations.cu:412-419.  dst u32[rows][nttLen] (all outputs, % p) */
 int cuhe_intt_double_deg(cuhe_ctx* ctx, uint32_t* dst, const uint64_t* src, int lvl, cuhe_stream stream);

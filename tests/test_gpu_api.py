@@ -118,6 +118,13 @@ def test_cand_cxor_cnot(ch):
     mraw[:o.n] = m
     want = orc.ntt_mul(o.ntt(rb), np.broadcast_to(orc.ntt_ext(mraw, o.N), (o.L(0), o.N)).copy())
     assert np.array_equal(u64(prod.nRep()), want)
+    # plaintext domain machine: level -1 is one residue (cuhe/Parameters.cu:107-109)
+    pt2 = ch.CuPtxt()
+    pt2.setLogq(ch.param.logMsg, 0, m)
+    pt2.x2n()
+    assert pt2.nRep().shape[0] == 1
+    pt2.x2z()
+    assert pt2.zRep() == m
 
 
 def test_relin_modswitch_chain(ch):
