@@ -82,6 +82,11 @@ struct cuhe_ctx {
     uint32_t* d_m_crt = nullptr;
     // fast reduction modulo Phi_m (needs Phi | x^m - 1): quotient through an Nq-point product,
     // q*Phi through an Nr-point product; tables for the local rows of level 0
+    // both NTT passes in one persistent thread-block-cluster launch (CUHE_B200_NTT_FUSED=1).  Off by
+    // default: measured 17 % slower than two launches on B200 (1.13 M vs 1.36 M 64K transforms/s) --
+    // the two cluster barriers per transform cost more than the saved DRAM round trip, which the
+    // ALU-bound kernels were not waiting for anyway.
+    bool use_fused = false;
     bool fast_reduce = false;
     int Nq = 0, Nr = 0, k1 = 0;            // k1 = m - n quotient coefficients
     uint64_t *d_tq = nullptr, *d_tr = nullptr;
@@ -149,20 +154,38 @@ static const NttPlan& get_plan(cuhe_ctx* c, int N) {
 }
 
 // ---- transform drivers -------------------------------------------------------
+// Runs pass 1 + pass 2 for `count` transforms.  Fused path: one launch of persistent thread-block
+// clusters whose N-word intermediates live in a small reused (L2-resident) slot array; split path:
+// two launches through a count*N-word scratch.  a.scratch / b.scratch are filled in here.
+static void run_ntt(cuhe_ctx* c, const NttPlan& pl, int mode, int out, Pass1Args a, Pass2Args b, int count,
+                    cudaStream_t st) {
+    if (count <= 0) return;
+    if (c->use_fused) {
+        Tmp slots(c, (size_t)fused_slots(pl.r3) * pl.N * 8, st);
+        a.scratch = slots.as<uint64_t>(); b.scratch = slots.as<uint64_t>();
+        cudaError_t e = launch_fused(pl.r3, mode, out, a, b, count, st);
+        if (e == cudaSuccess) return;
+        if (e != cudaErrorNotSupported) throw CudaFail{e, "launch_fused", __LINE__};
+        cudaGetLastError();
+    }
+    Tmp scratch(c, (size_t)count * pl.N * 8, st);
+    a.scratch = scratch.as<uint64_t>(); b.scratch = scratch.as<uint64_t>();
+    CK(launch_pass1(mode, a, count, st));
+    CK(launch_pass2(pl.r3, out, b, count, st));
+}
+
 // forward zero-padded transform of `count` polynomials.
 //   src: u32, polynomial t at src + t*src_stride (+ offset), crtLen = N/2 words read
 //   mul_tab != null: outputs multiplied by mul_tab[t % row_mod][.]
 static void fwd_ntt(cuhe_ctx* c, int N, uint64_t* dst, const uint32_t* src, long long src_stride, int count,
                     const uint64_t* mul_tab, int row_mod, cudaStream_t st) {
     const NttPlan& pl = get_plan(c, N);
-    Tmp scratch(c, (size_t)count * N * 8, st);
     Pass1Args a{};
-    a.scratch = scratch.as<uint64_t>(); a.src = src; a.tw1 = pl.tw1; a.src_stride = src_stride; a.n2 = pl.n2;
-    CK(launch_pass1(IN_EXT_U32, a, count, st));
+    a.src = src; a.tw1 = pl.tw1; a.src_stride = src_stride; a.n2 = pl.n2;
     Pass2Args b{};
-    b.dst = dst; b.scratch = scratch.as<uint64_t>(); b.tw2 = pl.tw2; b.mul_tab = mul_tab; b.dst_stride = N;
+    b.dst = dst; b.tw2 = pl.tw2; b.mul_tab = mul_tab; b.dst_stride = N;
     b.row_mod = row_mod > 0 ? row_mod : 1;
-    CK(launch_pass2(pl.r3, mul_tab ? OUT_U64_MUL : OUT_U64, b, count, st));
+    run_ntt(c, pl, IN_EXT_U32, mul_tab ? OUT_U64_MUL : OUT_U64, a, b, count, st);
 }
 // forward transform whose zero-padded input is gathered (and optionally folded mod x^m - 1):
 // x[j] = src[t*stride + base + dir*j] (+ src[.. + fold_m] mod p), j < len
@@ -170,30 +193,26 @@ static void fwd_ntt_map(cuhe_ctx* c, int N, uint64_t* dst, const uint32_t* src, 
                         int len, int base, int dir, int fold_m, int fold_lim, const uint64_t* mul_tab, int row_mod,
                         cudaStream_t st) {
     const NttPlan& pl = get_plan(c, N);
-    Tmp scratch(c, (size_t)count * N * 8, st);
     Pass1Args a{};
-    a.scratch = scratch.as<uint64_t>(); a.src = src; a.tw1 = pl.tw1; a.src_stride = src_stride; a.n2 = pl.n2;
+    a.src = src; a.tw1 = pl.tw1; a.src_stride = src_stride; a.n2 = pl.n2;
     a.map_len = len; a.map_base = base; a.map_dir = dir; a.fold_m = fold_m; a.fold_lim = fold_lim;
     a.primes = c->d_primes; a.prime_base = c->rank; a.prime_step = c->world; a.row_mod = row_mod > 0 ? row_mod : 1;
-    CK(launch_pass1(IN_U32_MAP, a, count, st));
     Pass2Args b{};
-    b.dst = dst; b.scratch = scratch.as<uint64_t>(); b.tw2 = pl.tw2; b.mul_tab = mul_tab; b.dst_stride = N;
+    b.dst = dst; b.tw2 = pl.tw2; b.mul_tab = mul_tab; b.dst_stride = N;
     b.row_mod = row_mod > 0 ? row_mod : 1;
-    CK(launch_pass2(pl.r3, mul_tab ? OUT_U64_MUL : OUT_U64, b, count, st));
+    run_ntt(c, pl, IN_U32_MAP, mul_tab ? OUT_U64_MUL : OUT_U64, a, b, count, st);
 }
 // inverse transform + % p of `count` = k*rows transforms -> u32[count][N] (all outputs)
 static void inv_ntt_modp(cuhe_ctx* c, int N, uint32_t* dst, const uint64_t* src, const uint64_t* src2, int count,
                          int row_mod, cudaStream_t st) {
     const NttPlan& pl = get_plan(c, N);
-    Tmp scratch(c, (size_t)count * N * 8, st);
     Pass1Args a{};
-    a.scratch = scratch.as<uint64_t>(); a.src = src; a.src2 = src2; a.tw1 = pl.tw1s;
+    a.src = src; a.src2 = src2; a.tw1 = pl.tw1s;
     a.src_stride = N; a.src2_stride = N; a.n2 = pl.n2;
-    CK(launch_pass1(src2 ? IN_U64_REV_MUL : IN_U64_REV, a, count, st));
     Pass2Args b{};
-    b.dst = dst; b.scratch = scratch.as<uint64_t>(); b.tw2 = pl.tw2; b.primes = c->d_primes; b.mus = c->d_mus;
+    b.dst = dst; b.tw2 = pl.tw2; b.primes = c->d_primes; b.mus = c->d_mus;
     b.dst_stride = N; b.prime_base = c->rank; b.prime_step = c->world; b.row_mod = row_mod > 0 ? row_mod : 1;
-    CK(launch_pass2(pl.r3, OUT_U32_MODP, b, count, st));
+    run_ntt(c, pl, src2 ? IN_U64_REV_MUL : IN_U64_REV, OUT_U32_MODP, a, b, count, st);
 }
 
 // `batch` polynomials, each `rows` residues: hold u32[batch*rows][N] -> dst u32[batch*rows][H]
@@ -459,6 +478,7 @@ int cuhe_ctx_create(cuhe_ctx** out, const cuhe_params* p, int device, int shard_
                     chk.logCrtPrime == p->logCrtPrime && chk.numEvalKey == p->numEvalKey,
                 "cuhe_params was not produced by cuhe_set_parameters");
         c->device = device; c->rank = shard_rank; c->world = shard_world;
+        { const char* sp = getenv("CUHE_B200_NTT_FUSED"); c->use_fused = (sp && sp[0] == '1'); }
         DeviceGuard dg(device);
         // pool: replaces DeviceAllocator (cuhe/DeviceManager.cu:36-138)
         cudaMemPoolProps props{};
@@ -820,14 +840,13 @@ int cuhe_relin(cuhe_ctx* c, uint64_t* dst, const uint32_t* raw, int lvl, cuhe_st
         if (rows == 0) return;
         const NttPlan& pl = get_plan(c, N);
         // digit transforms, prime independent (nttw, cuhe/Operations.cu:399-403)
-        Tmp D(c, (size_t)K * N * 8, st), scratch(c, (size_t)K * N * 8, st);
+        Tmp D(c, (size_t)K * N * 8, st);
         Pass1Args a{};
-        a.scratch = scratch.as<uint64_t>(); a.src = raw; a.tw1 = pl.tw1; a.n2 = pl.n2;
+        a.src = raw; a.tw1 = pl.tw1; a.n2 = pl.n2;
         a.digit_w = c->par.logRelin; a.digit_words = c->par.wordsCoeffAt(lvl); a.digit_first = 0;
-        CK(launch_pass1(IN_DIGIT, a, K, st));
         Pass2Args b{};
-        b.dst = D.as<uint64_t>(); b.scratch = scratch.as<uint64_t>(); b.tw2 = pl.tw2; b.dst_stride = N; b.row_mod = 1;
-        CK(launch_pass2(pl.r3, OUT_U64, b, K, st));
+        b.dst = D.as<uint64_t>(); b.tw2 = pl.tw2; b.dst_stride = N; b.row_mod = 1;
+        run_ntt(c, pl, IN_DIGIT, OUT_U64, a, b, K, st);
         dim3 grid((N + 255) / 256, rows);
         relin_mac_kernel<<<grid, 256, 0, st>>>(dst, D.as<uint64_t>(), c->d_ek, K, (long long)N, (long long)K0 * N, 0, 1, N);
         count_launch();
@@ -849,13 +868,11 @@ int cuhe_intt_batch(cuhe_ctx* c, uint64_t* dst, const uint64_t* src, int nttLen,
         DeviceGuard dg(c->device);
         cudaStream_t st = (cudaStream_t)stream;
         const NttPlan& pl = get_plan(c, nttLen);
-        Tmp scratch(c, (size_t)count * nttLen * 8, st);
         Pass1Args a{};
-        a.scratch = scratch.as<uint64_t>(); a.src = src; a.tw1 = pl.tw1s; a.src_stride = nttLen; a.n2 = pl.n2;
-        CK(launch_pass1(IN_U64_REV, a, count, st));
+        a.src = src; a.tw1 = pl.tw1s; a.src_stride = nttLen; a.n2 = pl.n2;
         Pass2Args b{};
-        b.dst = dst; b.scratch = scratch.as<uint64_t>(); b.tw2 = pl.tw2; b.dst_stride = nttLen; b.row_mod = 1;
-        CK(launch_pass2(pl.r3, OUT_U64, b, count, st));
+        b.dst = dst; b.tw2 = pl.tw2; b.dst_stride = nttLen; b.row_mod = 1;
+        run_ntt(c, pl, IN_U64_REV, OUT_U64, a, b, count, st);
     });
 }
 

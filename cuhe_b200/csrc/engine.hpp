@@ -49,6 +49,11 @@ struct Pass2Args {
 };
 cudaError_t launch_pass1(int mode, const Pass1Args& a, int count, cudaStream_t st);
 cudaError_t launch_pass2(int r3, int out, const Pass2Args& a, int count, cudaStream_t st);
+// both passes in one launch (persistent thread-block clusters, L2-resident intermediate).
+// a.scratch / b.scratch must point at `fused_slots(r3)` * N words.  Returns cudaErrorNotSupported for a
+// (mode, out) pair that is not instantiated.
+int fused_slots(int r3);
+cudaError_t launch_fused(int r3, int mode, int out, const Pass1Args& a, const Pass2Args& b, int count, cudaStream_t st);
 
 // which primes the rows of a [rows][..] array refer to
 struct PrimeView {

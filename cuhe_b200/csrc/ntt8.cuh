@@ -55,14 +55,14 @@ __device__ __forceinline__ void twiddle8_dyn(uint64_t (&x)[8], int i) {
 // 8 x 8, then the table multiply by w^(k1*j2).
 //   X[a + 8b] = sum_i w8^(ib) * 2^(3ia) * sum_k x[i + 8k] w8^(ka)
 // ---------------------------------------------------------------------------
+// S8: [64][T] words of shared memory (column of thread tid at S8[.][tid]); t = transform index;
+// j2_base = first column of this CTA; `out` = where transform t's pass-1 result goes ([N] words)
 template <int MODE>
-__global__ void __launch_bounds__(CUHE_P1V2_THREADS) ntt_pass1_v2_kernel(Pass1Args a) {
+__device__ __forceinline__ void ntt_pass1_body(const Pass1Args& a, uint64_t* S8, int t, int j2_base, uint64_t* out) {
     constexpr int T = CUHE_P1V2_THREADS;
     constexpr bool EXT = (MODE == IN_EXT_U32 || MODE == IN_DIGIT || MODE == IN_U32_MAP);
-    extern __shared__ uint64_t S8[];                 // [64][T], column of thread tid at S8[.][tid]
     const int tid = threadIdx.x;
-    const int j2 = blockIdx.x * T + tid;
-    const int t = blockIdx.y;
+    const int j2 = j2_base + tid;
     const int n2 = a.n2;
     const int N = n2 * 64;
     uint64_t* col = S8 + tid;
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(CUHE_P1V2_THREADS) ntt_pass1_v2_kernel(Pass1Ar
 #pragma unroll
         for (int r = 0; r < 8; r++) col[(bitrev(r, 3) * 8 + i) * T] = x[r];
     }
-    uint64_t* d = a.scratch + (long long)t * N + j2;
+    uint64_t* d = out + j2;
     const uint64_t* tw = a.tw1 + j2;
 #pragma unroll 1
     for (int aa = 0; aa < 8; aa++) {
@@ -155,6 +155,12 @@ __global__ void __launch_bounds__(CUHE_P1V2_THREADS) ntt_pass1_v2_kernel(Pass1Ar
         for (int r = 0; r < 8; r++) d[(aa + 8 * bitrev(r, 3)) * n2] = mul_modP(x[r], w[r]);
     }
 }
+template <int MODE>
+__global__ void __launch_bounds__(CUHE_P1V2_THREADS) ntt_pass1_v2_kernel(Pass1Args a) {
+    extern __shared__ uint64_t S8[];
+    const int t = blockIdx.y;
+    ntt_pass1_body<MODE>(a, S8, t, blockIdx.x * CUHE_P1V2_THREADS, a.scratch + (long long)t * a.n2 * 64);
+}
 
 // ---------------------------------------------------------------------------
 // pass 2: CTA = tile of R = 128/R3 rows k1 (contiguous N2 words each).
@@ -164,18 +170,17 @@ __global__ void __launch_bounds__(CUHE_P1V2_THREADS) ntt_pass1_v2_kernel(Pass1Ar
 //           natural-order scatter X[k1 + 64*(k2a + 64*k2b)], lanes along k1
 // The phase-A result for k2a = a + 8b sits at position a*8 + b of its column.
 // ---------------------------------------------------------------------------
+// sm: padded shared tile; t = transform index; r0 = first row of this CTA's tile;
+// `in` = transform t's pass-1 result ([N] words)
 template <int R3, int OUT>
-__global__ void __launch_bounds__(128) ntt_pass2_v2_kernel(Pass2Args a) {
+__device__ __forceinline__ void ntt_pass2_body(const Pass2Args& a, uint64_t* sm, int t, int r0, const uint64_t* in_t) {
     using Cfg = Pass2Cfg<R3>;
     constexpr int R = Cfg::R, KS = Cfg::KS, RS = Cfg::RS;
     constexpr int N2 = 64 * R3, N = 64 * N2;
-    extern __shared__ uint64_t sm[];
-    const int t = blockIdx.y;
-    const int r0 = blockIdx.x * R;
     const int tid = threadIdx.x;
     {
         const int j2b = tid % R3, row = tid / R3;
-        const uint64_t* s = a.scratch + (long long)t * N + (long long)(r0 + row) * N2 + j2b;
+        const uint64_t* s = in_t + (long long)(r0 + row) * N2 + j2b;
         uint64_t* col = sm + row * RS + j2b;
         uint64_t nx[8];
 #pragma unroll
@@ -187,7 +192,7 @@ __global__ void __launch_bounds__(128) ntt_pass2_v2_kernel(Pass2Args a) {
             for (int k = 0; k < 8; k++) x[k] = nx[k];
             if (i < 7) {
 #pragma unroll
-                for (int k = 0; k < 8; k++) nx[k] = s[(i + 1 + 8 * k) * R3];
+                for (int k = 0; k < 8; k++) nx[k] = __ldcg(s + (i + 1 + 8 * k) * R3);
             }
             ntt_regs<8, false>(x);
             twiddle8_dyn(x, i);
@@ -244,6 +249,52 @@ __global__ void __launch_bounds__(128) ntt_pass2_v2_kernel(Pass2Args a) {
                 }
             }
         }
+    }
+}
+template <int R3, int OUT>
+__global__ void __launch_bounds__(128) ntt_pass2_v2_kernel(Pass2Args a) {
+    extern __shared__ uint64_t sm[];
+    constexpr int N = 64 * 64 * R3;
+    const int t = blockIdx.y;
+    ntt_pass2_body<R3, OUT>(a, sm, t, blockIdx.x * Pass2Cfg<R3>::R, a.scratch + (long long)t * N);
+}
+
+// ---------------------------------------------------------------------------
+// Fused transform: one thread-block CLUSTER per transform, both passes in one
+// launch.  The cluster has CS = N2/128 = 64/R CTAs (8 / 4 / 2 for 64K / 32K /
+// 16K): in pass 1 CTA r owns columns [128r, 128r+128), in pass 2 the row tile
+// [R*r, R*r+R).  The N-word intermediate lives in a per-cluster slot of global
+// memory that is written, cluster-synchronised and re-read within microseconds
+// and then reused for the cluster's next transform, so it stays in the 126 MB L2
+// (no DRAM round trip: one HBM read of the input and one write of the output per
+// transform).  Clusters are persistent: grid = resident clusters, loop over t.
+// ---------------------------------------------------------------------------
+template <int R3>
+struct FusedCfg {
+    static constexpr int CS = 64 / Pass2Cfg<R3>::R;                      // cluster size
+    static constexpr int SMEM1 = 64 * CUHE_P1V2_THREADS * 8;
+    static constexpr int SMEM = SMEM1 > Pass2Cfg<R3>::SMEM ? SMEM1 : Pass2Cfg<R3>::SMEM;
+};
+__device__ __forceinline__ void cluster_sync_all() {
+    // release/acquire at cluster scope: the pass-1 stores of every CTA of the cluster are visible
+    // to the pass-2 loads of every other CTA afterwards
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <int R3, int MODE, int OUT>
+__global__ void __launch_bounds__(128) ntt_fused_kernel(Pass1Args a, Pass2Args b, int count) {
+    static_assert(CUHE_P1V2_THREADS == 128, "fused kernel assumes 128 columns per CTA");
+    using F = FusedCfg<R3>;
+    constexpr int N = 64 * 64 * R3;
+    extern __shared__ uint64_t smf[];
+    const int rank = blockIdx.x % F::CS;                 // %cluster_ctarank for a 1-D cluster
+    const int cid = blockIdx.x / F::CS;
+    const int ncl = gridDim.x / F::CS;
+    uint64_t* slot = a.scratch + (long long)cid * N;     // this cluster's L2-resident intermediate
+    for (int t = cid; t < count; t += ncl) {
+        ntt_pass1_body<MODE>(a, smf, t, rank * 128, slot);
+        cluster_sync_all();
+        ntt_pass2_body<R3, OUT>(b, smf, t, rank * Pass2Cfg<R3>::R, slot);
+        cluster_sync_all();                              // slot and shared memory are reused by the next t
     }
 }
 

@@ -85,4 +85,80 @@ cudaError_t launch_pass2(int r3, int out, const Pass2Args& a, int count, cudaStr
     return cudaErrorInvalidValue;
 }
 
+
+// ---- fused cluster launch ---------------------------------------------------------
+template <int R3, int MODE, int OUT>
+static int fused_max_clusters() {
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && cached[dev]) return cached[dev];
+    using F = FusedCfg<R3>;
+    auto* fn = ntt_fused_kernel<R3, MODE, OUT>;
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM) != cudaSuccess) return 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(F::CS, 1, 1);
+    cfg.blockDim = dim3(128, 1, 1);
+    cfg.dynamicSmemBytes = F::SMEM;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = F::CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, fn, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); return 0; }
+    if (dev < 64) cached[dev] = n;
+    return n;
+}
+template <int R3, int MODE, int OUT>
+static cudaError_t launch_fused_t(const Pass1Args& a, const Pass2Args& b, int count, cudaStream_t st) {
+    using F = FusedCfg<R3>;
+    int ncl = fused_max_clusters<R3, MODE, OUT>();
+    if (ncl <= 0) return cudaErrorNotSupported;
+    const int slots = fused_slots(R3);
+    if (ncl > slots) ncl = slots;
+    if (ncl > count) ncl = count;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ncl * F::CS, 1, 1);
+    cfg.blockDim = dim3(128, 1, 1);
+    cfg.dynamicSmemBytes = F::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = F::CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, ntt_fused_kernel<R3, MODE, OUT>, a, b, count);
+    count_launch();
+    return e;
+}
+// intermediate slots per transform length: enough for every co-resident cluster (148 SMs x 3 CTAs / CS),
+// 56 x 512 KB = 28 MB at 64K -- a small fraction of the 126 MB L2
+int fused_slots(int r3) { return r3 == 16 ? 56 : (r3 == 8 ? 112 : 224); }
+
+template <int R3>
+static cudaError_t launch_fused_r3(int mode, int out, const Pass1Args& a, const Pass2Args& b, int count, cudaStream_t st) {
+#define CUHE_FUSED_CASE(M, O) if (mode == M && out == O) return launch_fused_t<R3, M, O>(a, b, count, st)
+    CUHE_FUSED_CASE(IN_EXT_U32, OUT_U64);
+    CUHE_FUSED_CASE(IN_EXT_U32, OUT_U64_MUL);
+    CUHE_FUSED_CASE(IN_DIGIT, OUT_U64);
+    CUHE_FUSED_CASE(IN_U64_REV, OUT_U32_MODP);
+    CUHE_FUSED_CASE(IN_U64_REV_MUL, OUT_U32_MODP);
+    CUHE_FUSED_CASE(IN_U64_REV, OUT_U64);
+    CUHE_FUSED_CASE(IN_U32_MAP, OUT_U64_MUL);
+#undef CUHE_FUSED_CASE
+    return cudaErrorNotSupported;
+}
+cudaError_t launch_fused(int r3, int mode, int out, const Pass1Args& a, const Pass2Args& b, int count, cudaStream_t st) {
+    if (count <= 0) return cudaSuccess;
+#ifdef CUHE_NTT_V1
+    return cudaErrorNotSupported;
+#else
+    switch (r3) {
+        case 4: return launch_fused_r3<4>(mode, out, a, b, count, st);
+        case 8: return launch_fused_r3<8>(mode, out, a, b, count, st);
+        case 16: return launch_fused_r3<16>(mode, out, a, b, count, st);
+    }
+    return cudaErrorInvalidValue;
+#endif
+}
+
 }  // namespace cuhe_b200

@@ -426,3 +426,27 @@ def test_full_size_c2_properties(lib):
         assert np.array_equal(Eng.dn(c1, np.uint32), Eng.dn(c2, np.uint32))
     finally:
         e.close()
+
+
+def test_fused_cluster_ntt_matches(lib, monkeypatch):
+    """The optional one-launch transform (persistent thread-block clusters, CUHE_B200_NTT_FUSED=1)
+    gives the same bits as the default two-launch path: forward, inverse and a whole multiply."""
+    monkeypatch.setenv("CUHE_B200_NTT_FUSED", "1")
+    e = Eng(lib, MID64K)
+    try:
+        o = e.orc
+        from oracle import oracle as orc
+        N = o.N
+        rng = np.random.default_rng(77)
+        x = rng.integers(0, 1 << 31, size=(5, N), dtype=np.uint32)
+        out = e.empty((5, N), np.uint64)
+        e.call("cuhe_ntt_ext_batch", p(out), p(e.up(x)), N, 5, C.c_longlong(N), e.st())
+        assert np.array_equal(Eng.dn(out, np.uint64), orc.ntt_ext(x, N))
+        _, ra = rand_poly_raw(o, 0, 1)
+        _, rb = rand_poly_raw(o, 0, 2)
+        res = np.zeros_like(ra)
+        e.call("cuhe_mul_raw_host", res.ctypes.data_as(C.c_void_p), ra.ctypes.data_as(C.c_void_p),
+               rb.ctypes.data_as(C.c_void_p), 0, e.st())
+        assert np.array_equal(res, o.icrt(o.mul_raw_to_crt(ra, rb, 0), 0))
+    finally:
+        e.close()
