@@ -326,7 +326,7 @@ static void launch_icrt(uint32_t* dst, const uint32_t* src, cuhe_ctx* c, const I
         icrt_kernel<WMAX><<<grid, 128, 0, st>>>(dst, src, c->d_primes, c->d_mus, ic.M, ic.mi, ic.bi, ic.L, ic.W, ic.Wp, b,
                                                 e, c->par.crtLen);
     } else {
-        const size_t smem = ((size_t)ic.L * ic.Wp + ic.W) * 4;
+        const size_t smem = ((size_t)ic.L * ((ic.Wp + 3) & ~3) + ic.W) * 4;
         icrt_kernel_v2<WMAX><<<grid, 128, smem, st>>>(dst, src, c->d_primes, c->d_mus, ic.M, ic.mi, ic.bi, ic.m_top, ic.L,
                                                       ic.W, ic.Wp, b, e, c->par.crtLen);
     }

@@ -199,33 +199,40 @@ __global__ void __launch_bounds__(128)
 icrt_kernel_v2(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, const uint32_t* __restrict__ primes,
                const uint64_t* __restrict__ mus, const uint32_t* __restrict__ M, const uint32_t* __restrict__ mi,
                const uint32_t* __restrict__ bi, double m_top, int L, int W, int Wp, int i_begin, int i_end, int H) {
-    extern __shared__ uint32_t sh[];          // [L][Wp] M_l, [W] M
+    extern __shared__ uint32_t sh[];          // [L][Wp4] M_l (rows zero-padded to 4 words), [W] M
+    const int Wp4 = (Wp + 3) & ~3;
     uint32_t* smi = sh;
-    uint32_t* sM = sh + L * Wp;
-    for (int e = threadIdx.x; e < L * Wp; e += 128) smi[e] = mi[e];
+    uint32_t* sM = sh + L * Wp4;
+    for (int e = threadIdx.x; e < L * Wp4; e += 128) {
+        const int l = e / Wp4, k = e - l * Wp4;
+        smi[e] = k < Wp ? mi[(long long)l * Wp + k] : 0u;
+    }
     for (int e = threadIdx.x; e < W; e += 128) sM[e] = M[e];
     __syncthreads();
     const int idx = i_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= i_end) return;
     src += (long long)blockIdx.y * L * H;
     dst += (long long)blockIdx.y * H * W;
-    uint32_t sum[WMAX + 1];
+    uint32_t sum[WMAX + 4];
 #pragma unroll
-    for (int k = 0; k <= WMAX; k++) sum[k] = 0;
+    for (int k = 0; k < WMAX + 4; k++) sum[k] = 0;
     for (int l = 0; l < L; l++) {
         const uint32_t p = primes[l];
         const uint64_t mu = mus[l];
         const uint64_t tar = mod_u64_u32(src[(long long)l * H + idx], p, mu);
         const uint32_t tt = mod_u64_u32(tar * bi[l], p, mu);
-        const uint32_t* m = smi + l * Wp;
+        const uint32_t* m = smi + l * Wp4;
         uint64_t carry = 0;
 #pragma unroll
-        for (int k = 0; k <= WMAX; k++) {
+        for (int k = 0; k < WMAX + 4; k += 4) {      // one 128-bit broadcast load per four multiply-adds
             if (k <= W) {
-                uint64_t t = (uint64_t)sum[k] + carry;
-                if (k < Wp) t += (uint64_t)tt * m[k];
-                sum[k] = (uint32_t)t;
-                carry = t >> 32;
+                uint4 q = make_uint4(0u, 0u, 0u, 0u);
+                if (k < Wp4) q = *reinterpret_cast<const uint4*>(m + k);
+                uint64_t t;
+                t = (uint64_t)sum[k] + carry + (uint64_t)tt * q.x;     sum[k] = (uint32_t)t;     carry = t >> 32;
+                t = (uint64_t)sum[k + 1] + carry + (uint64_t)tt * q.y; sum[k + 1] = (uint32_t)t; carry = t >> 32;
+                t = (uint64_t)sum[k + 2] + carry + (uint64_t)tt * q.z; sum[k + 2] = (uint32_t)t; carry = t >> 32;
+                t = (uint64_t)sum[k + 3] + carry + (uint64_t)tt * q.w; sum[k + 3] = (uint32_t)t; carry = t >> 32;
             }
         }
     }
