@@ -23,6 +23,13 @@
 
 namespace cuhe_b200 {
 
+// read-only 64-bit load that stays where it is written (software prefetch into registers)
+__device__ __forceinline__ uint64_t ld_nc_u64(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+
 // x[r] *= 2^(3 * I * bitrev3(r)): the twiddle between the two radix-8 layers
 template <int I, int... R>
 __device__ __forceinline__ void twiddle8_seq(uint64_t (&x)[8], std::integer_sequence<int, R...>) {
@@ -143,11 +150,21 @@ __device__ __forceinline__ void ntt_pass1_body(const Pass1Args& a, uint64_t* S8,
     }
     uint64_t* d = out + j2;
     const uint64_t* tw = a.tw1 + j2;
+    // the 8 table twiddles of iteration aa+1 are requested before iteration aa is transformed
+    // (volatile asm keeps the loads where they are written; the compiler otherwise sinks them next to
+    // their uses and the L2 latency shows up as long_scoreboard stalls)
+    uint64_t wn[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) wn[r] = ld_nc_u64(tw + (8 * bitrev(r, 3)) * n2);
 #pragma unroll 1
     for (int aa = 0; aa < 8; aa++) {
         uint64_t x[8], w[8];
 #pragma unroll
-        for (int r = 0; r < 8; r++) w[r] = __ldg(tw + (aa + 8 * bitrev(r, 3)) * n2);   // in flight during the butterfly
+        for (int r = 0; r < 8; r++) w[r] = wn[r];
+        if (aa < 7) {
+#pragma unroll
+            for (int r = 0; r < 8; r++) wn[r] = ld_nc_u64(tw + (aa + 1 + 8 * bitrev(r, 3)) * n2);
+        }
 #pragma unroll
         for (int i = 0; i < 8; i++) x[i] = col[(aa * 8 + i) * T];
         ntt_regs<8, false>(x);                       // over i -> b = bitrev3(r)
@@ -200,18 +217,23 @@ __device__ __forceinline__ void ntt_pass2_body(const Pass2Args& a, uint64_t* sm,
             for (int r = 0; r < 8; r++) col[(bitrev(r, 3) * 8 + i) * KS] = x[r];
         }
         const uint64_t* tw = a.tw2 + j2b;
+        uint64_t wn[8];                                   // twiddles of the next iteration, prefetched
+#pragma unroll
+        for (int r = 0; r < 8; r++) wn[r] = ld_nc_u64(tw + (8 * bitrev(r, 3)) * R3);
 #pragma unroll 1
         for (int aa = 0; aa < 8; aa++) {
-            uint64_t x[8];
+            uint64_t x[8], w[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) w[r] = wn[r];
+            if (aa < 7) {
+#pragma unroll
+                for (int r = 0; r < 8; r++) wn[r] = ld_nc_u64(tw + (aa + 1 + 8 * bitrev(r, 3)) * R3);
+            }
 #pragma unroll
             for (int i = 0; i < 8; i++) x[i] = col[(aa * 8 + i) * KS];
             ntt_regs<8, false>(x);
 #pragma unroll
-            for (int r = 0; r < 8; r++) {
-                const int b = bitrev(r, 3);
-                const int k2a = aa + 8 * b;
-                col[(aa * 8 + b) * KS] = mul_modP(x[r], __ldg(tw + k2a * R3));
-            }
+            for (int r = 0; r < 8; r++) col[(aa * 8 + bitrev(r, 3)) * KS] = mul_modP(x[r], w[r]);
         }
     }
     __syncthreads();
