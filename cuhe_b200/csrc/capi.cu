@@ -520,7 +520,6 @@ int cuhe_ctx_create(cuhe_ctx** out, const cuhe_params* p, int device, int shard_
             d.M = upload(ic.M); d.mi = upload(ic.mi); d.bi = upload(ic.bi);
             c->icrt[lvl] = d;
         }
-        CK(cudaFuncSetAttribute(crt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         get_plan(c.get(), c->par.nttLen);
         CK(cudaDeviceSynchronize());
         *out = c.release();

@@ -1,15 +1,17 @@
 // cuhe_b200/csrc/ntt8.cuh
-// NTT pass kernels, generation 2: the same two-pass decomposition as ntt.cuh
-//   N = 64 * N2,  N2 = 64 * R3,  R3 in {4, 8, 16}
-// but every 64-point column transform is run as 8 x 8: two layers of radix-8
-// register butterflies, the column itself parked in a thread-private strip of
-// shared memory between the layers.  Rationale (profiles/r01_ntt_v1_*): the
-// fully unrolled radix-64 of ntt.cuh is ~8100 SASS instructions (130 KB) per
-// kernel, larger than the instruction caches, and ncu attributes most issue
-// stalls to "no_instruction"; it also needs ~200 registers (8 warps/SM).
-// Here the loop bodies are one radix-8 (compile-time shift twiddles) plus a
-// warp-uniform switch over the 8 inter-layer twiddle patterns 2^(3*i*a), so
-// the hot code is ~20 KB and a thread needs ~64 registers.
+// Batched NTT / inverse NTT modulo P = 2^64 - 2^32 + 1 for sm_100a.
+//
+// Replaces the reference's 18 per-size kernels ntt_{1,2,3}_{16k,32k,64k}[_ext[_block]] /
+// intt_{1,3}_* (cuhe/Base.cu:309-842) and their per-residue host loops
+// (cuhe/Operations.cu:306-434).  Same transform (tests/test_ntt.cu:38-64: cyclic, natural order
+// in and out, X[i] = sum_j x[j] w^(ij), w = g^(65536/N)), different machine mapping:
+//   N = 64 * N2,  N2 = 64 * R3,  R3 in {4, 8, 16}   (N = 16384 / 32768 / 65536)
+// two passes, one launch each for every {residue x polynomial} transform of the call
+// (grid.y = count) instead of 3 launches per residue.  Every 64-point column transform runs as
+// 8 x 8: two layers of radix-8 register butterflies, the column parked in a thread-private strip
+// of shared memory between the layers.  The loop bodies are one radix-8 (compile-time shift
+// twiddles) plus a warp-uniform switch over the 8 inter-layer twiddle patterns 2^(3*i*a), so the
+// hot code is ~20 KB (fits the instruction caches) and a thread needs 40-130 registers.
 //
 // Lanes always run along independent columns, so every shift amount is either a
 // compile-time constant or uniform across the warp -- the per-thread `switch`

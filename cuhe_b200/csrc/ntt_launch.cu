@@ -19,17 +19,12 @@ static cudaError_t set_smem_once(const void* fn, int bytes, bool* done) {
 
 template <int MODE>
 static cudaError_t launch_p1(const Pass1Args& a, int count, cudaStream_t st) {
-#ifdef CUHE_NTT_V1
-    dim3 grid(a.n2 / CUHE_P1_THREADS, count);
-    ntt_pass1_kernel<MODE><<<grid, CUHE_P1_THREADS, 0, st>>>(a);
-#else
     static bool done[64] = {false};
     constexpr int smem = 64 * CUHE_P1V2_THREADS * 8;
     cudaError_t e = set_smem_once((const void*)ntt_pass1_v2_kernel<MODE>, smem, done);
     if (e != cudaSuccess) return e;
     dim3 grid(a.n2 / CUHE_P1V2_THREADS, count);
     ntt_pass1_v2_kernel<MODE><<<grid, CUHE_P1V2_THREADS, smem, st>>>(a);
-#endif
     count_launch();
     return cudaGetLastError();
 }
@@ -41,9 +36,7 @@ cudaError_t launch_pass1(int mode, const Pass1Args& a, int count, cudaStream_t s
         case IN_DIGIT: return launch_p1<IN_DIGIT>(a, count, st);
         case IN_U64_REV: return launch_p1<IN_U64_REV>(a, count, st);
         case IN_U64_REV_MUL: return launch_p1<IN_U64_REV_MUL>(a, count, st);
-#ifndef CUHE_NTT_V1
         case IN_U32_MAP: return launch_p1<IN_U32_MAP>(a, count, st);
-#endif
     }
     return cudaErrorInvalidValue;
 }
@@ -52,11 +45,7 @@ template <int R3, int OUT>
 static cudaError_t launch_p2(const Pass2Args& a, int count, cudaStream_t st) {
     using Cfg = Pass2Cfg<R3>;
     static bool done[64] = {false};
-#ifdef CUHE_NTT_V1
-    auto* fn = ntt_pass2_kernel<R3, OUT>;
-#else
     auto* fn = ntt_pass2_v2_kernel<R3, OUT>;
-#endif
     cudaError_t e = set_smem_once((const void*)fn, Cfg::SMEM, done);
     if (e != cudaSuccess) return e;
     dim3 grid(64 / Cfg::R, count);
@@ -149,16 +138,12 @@ static cudaError_t launch_fused_r3(int mode, int out, const Pass1Args& a, const 
 }
 cudaError_t launch_fused(int r3, int mode, int out, const Pass1Args& a, const Pass2Args& b, int count, cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
-#ifdef CUHE_NTT_V1
-    return cudaErrorNotSupported;
-#else
     switch (r3) {
         case 4: return launch_fused_r3<4>(mode, out, a, b, count, st);
         case 8: return launch_fused_r3<8>(mode, out, a, b, count, st);
         case 16: return launch_fused_r3<16>(mode, out, a, b, count, st);
     }
     return cudaErrorInvalidValue;
-#endif
 }
 
 }  // namespace cuhe_b200

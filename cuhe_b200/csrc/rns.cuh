@@ -20,50 +20,6 @@ namespace cuhe_b200 {
 __device__ __forceinline__ int prime_index(const PrimeView& v, int row) { return v.base + v.step * row; }
 
 // ---------------------------------------------------------------------------
-// CRT: raw u32[H][W] -> u32[rows][H].                       (cuhe/Base.cu:857-879)
-// residue = sum_k word_k * (2^(32k) mod p)  mod p, one 64-bit accumulator per
-// (coefficient, prime); pow32[l][k] = 2^(32k) mod p_l.  Only idx < n is written.
-// ---------------------------------------------------------------------------
-constexpr int kCrtThreads = 128;
-__global__ void __launch_bounds__(kCrtThreads)
-crt_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ raw, PrimeView pv, int rows,
-           const uint32_t* __restrict__ pow32, int pow_stride, int W, int n, int H) {
-    extern __shared__ uint32_t sw[];      // [kCrtThreads][W | 1]
-    const int ws = W | 1;                 // odd stride: conflict-free column reads
-    const int i0 = blockIdx.x * kCrtThreads;
-    const int cnt = min(kCrtThreads, H - i0);
-    raw += (long long)blockIdx.y * H * W;          // batch
-    dst += (long long)blockIdx.y * rows * H;
-    for (int e = threadIdx.x; e < cnt * W; e += kCrtThreads) {
-        int c = e / W, k = e - c * W;
-        sw[c * ws + k] = raw[(long long)i0 * W + e];
-    }
-    __syncthreads();
-    const int i = i0 + threadIdx.x;
-    if (i >= n) {
-        if (i < H) for (int r = 0; r < rows; r++) dst[(long long)r * H + i] = 0;
-        return;
-    }
-    const uint32_t* c = sw + threadIdx.x * ws;
-    for (int r = 0; r < rows; r++) {
-        const int l = prime_index(pv, r);
-        const uint32_t* pw = pow32 + (long long)l * pow_stride;
-        uint64_t acc = 0;                 // p < 2^26 (checked at init): 16 terms < 2^62
-        uint64_t acc_hi = 0;
-        for (int k = 0; k < W; k++) {
-            acc += (uint64_t)c[k] * __ldg(pw + k);
-            if ((k & 15) == 15) { acc_hi += acc >> 32; acc &= 0xFFFFFFFFull; }
-        }
-        // value = acc + acc_hi*2^32 ; fold with 2^32 mod p = pw[1]
-        const uint32_t p = pv.p[l];
-        const uint64_t mu = pv.mu[l];
-        uint64_t t = mod_u64_u32(acc_hi, p, mu);
-        uint64_t v = t * (W > 1 ? __ldg(pw + 1) : (uint32_t)((1ull << 32) % p)) + mod_u64_u32(acc, p, mu);
-        dst[(long long)r * H + i] = mod_u64_u32(v, p, mu);
-    }
-}
-
-// ---------------------------------------------------------------------------
 // ICRT: u32[L][H] -> raw u32[H][W]                          (cuhe/Base.cu:845-924)
 // coeff = sum_l ((c_l * b_l mod p_l) * M_l), one conditional subtraction of M
 // after every term (same accumulate / compare / subtract order as the
@@ -127,10 +83,11 @@ icrt_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, const 
 }
 
 // ---------------------------------------------------------------------------
-// CRT, generation 2: the W words of a coefficient live in registers (template
-// bucket WMAX), the table 2^(32k) mod p_l is staged in shared memory and read by
-// broadcast, so one IMAD.WIDE per (word, prime) remains (the first version issued
-// two loads per multiply-add and was LSU-bound).  Same result as crt_kernel.
+// CRT: raw u32[H][W] -> u32[rows][H]                          (cuhe/Base.cu:857-879)
+// residue = sum_k word_k * (2^(32k) mod p) mod p instead of the reference's Horner chain of
+// 64-bit `%`: the W words of a coefficient live in registers (template bucket WMAX), the table
+// 2^(32k) mod p_l is staged in shared memory and read by 128-bit broadcast loads, so one
+// IMAD.WIDE per (word, prime) remains.  Coefficients >= n are written as zero.
 // ---------------------------------------------------------------------------
 template <int WMAX>
 __global__ void __launch_bounds__(128)
