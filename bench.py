@@ -11,8 +11,8 @@ A "step" = one batch of B = batch x N_gpus independent ciphertext products, RAW 
 resident in HBM -> RAW product in HBM (crt x2, forward NTT x2L, fused pointwise
 mul + inverse NTT, polynomial Barrett (2 more forward + 2 more inverse NTTs per
 residue), ICRT).  With N > 1 the CRT-residue axis is sharded (rank r owns primes
-r, r+N, ...), the residues are all-gathered over NCCL before ICRT, ICRT is split
-by coefficient range and the RAW slices are all-gathered again.
+r, r+N, ...), ICRT is split by coefficient range: an NCCL all-to-all hands rank j the
+coefficient slice j of every residue, and the RAW slices are all-gathered.
 """
 from __future__ import annotations
 
@@ -202,6 +202,7 @@ def run_ours(args):
     crt_loc = torch.zeros((B, rows, H), dtype=torch.int32, device=dev)
     raw_out = torch.zeros((B, H, W), dtype=torch.int32, device=dev)
     cb, ce = sh.coefficient_slice(H, rank, world)
+    raw_slice = torch.zeros((B, ce - cb, W), dtype=torch.int32, device=dev)
     st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)  # noqa: E731
     p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
 
@@ -211,9 +212,10 @@ def run_ours(args):
         if world == 1:
             check(lib.cuhe_icrt_batch(h, p(raw_out), p(crt_loc), 0, 0, H, B, st()))
         else:
-            crt_all = sh.all_gather_residues(crt_loc, L, world)          # NCCL all-gather over NVLink
-            check(lib.cuhe_icrt_batch(h, p(raw_out), p(crt_all), 0, cb, ce, B, st()))
-            return sh.all_gather_raw(raw_out, rank, world)               # complete RAW on every rank
+            # NCCL all-to-all over NVLink: rank j receives coefficient slice j of every residue
+            crt_slice = sh.exchange_for_icrt(crt_loc, L, rank, world)
+            check(lib.cuhe_icrt_slice_batch(h, p(raw_slice), p(crt_slice), 0, cb, ce - cb, B, st()))
+            return sh.all_gather_raw_slices(raw_slice, world)            # complete RAW on every rank
 
     def barrier():
         if world > 1:

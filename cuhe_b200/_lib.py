@@ -69,6 +69,7 @@ SYMBOLS = {
     "cuhe_mul_raw_host_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "cuhe_mul_crt_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "cuhe_icrt_batch": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "cuhe_icrt_slice_batch": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "cuhe_modp_batch": (_i, [_vp, _i, _vp, _vp, _vp, C.c_size_t, _i, _vp]),
     "cuhe_launch_count": (_ll, [_i]),
 }

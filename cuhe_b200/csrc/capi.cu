@@ -319,16 +319,16 @@ __global__ void modp_batch_kernel(int op, uint64_t* __restrict__ out, const uint
 
 template <int WMAX>
 static void launch_icrt(uint32_t* dst, const uint32_t* src, cuhe_ctx* c, const IcrtDev& ic, int b, int e, int batch,
-                        cudaStream_t st) {
+                        int Hs, cudaStream_t st) {
     const int cnt = e - b;
     dim3 grid((cnt + 127) / 128, batch);
     if (ic.truncated) {
         icrt_kernel<WMAX><<<grid, 128, 0, st>>>(dst, src, c->d_primes, c->d_mus, ic.M, ic.mi, ic.bi, ic.L, ic.W, ic.Wp, b,
-                                                e, c->par.crtLen);
+                                                e, Hs);
     } else {
         const size_t smem = ((size_t)ic.L * ((ic.Wp + 3) & ~3) + ic.W) * 4;
         icrt_kernel_v2<WMAX><<<grid, 128, smem, st>>>(dst, src, c->d_primes, c->d_mus, ic.M, ic.mi, ic.bi, ic.m_top, ic.L,
-                                                      ic.W, ic.Wp, b, e, c->par.crtLen);
+                                                      ic.W, ic.Wp, b, e, Hs);
     }
     count_launch();
 }
@@ -348,18 +348,24 @@ static void launch_crt(cuhe_ctx* c, uint32_t* dst, const uint32_t* raw, int rows
     count_launch();
 }
 // ICRT of `batch` polynomials: crt_all u32[batch][L][H] -> raw u32[batch][H][W], coefficients [b,e)
+// Hs = words between consecutive residue rows (and coefficients per RAW polynomial) of the buffers:
+// crtLen for whole polynomials, the slice length for coefficient slices; [b,e) are indices into them
+static void do_icrt_strided(cuhe_ctx* c, uint32_t* raw_out, const uint32_t* crt_all, int lvl, int b, int e, int batch,
+                            int Hs, cudaStream_t st) {
+    if (b >= e || batch <= 0) return;
+    const IcrtDev& ic = c->icrt[lvl];
+    if (ic.W <= 8) launch_icrt<8>(raw_out, crt_all, c, ic, b, e, batch, Hs, st);
+    else if (ic.W <= 20) launch_icrt<20>(raw_out, crt_all, c, ic, b, e, batch, Hs, st);
+    else if (ic.W <= 36) launch_icrt<36>(raw_out, crt_all, c, ic, b, e, batch, Hs, st);
+    else if (ic.W <= 52) launch_icrt<52>(raw_out, crt_all, c, ic, b, e, batch, Hs, st);
+    else if (ic.W <= 104) launch_icrt<104>(raw_out, crt_all, c, ic, b, e, batch, Hs, st);
+    else throw ArgError{"coefficient modulus wider than 104 words"};
+    CK(cudaGetLastError());
+}
 static void do_icrt(cuhe_ctx* c, uint32_t* raw_out, const uint32_t* crt_all, int lvl, int b, int e, int batch,
                     cudaStream_t st) {
     if (e > c->par.modLen) e = c->par.modLen;     // the reference writes idx < modLen only
-    if (b >= e || batch <= 0) return;
-    const IcrtDev& ic = c->icrt[lvl];
-    if (ic.W <= 8) launch_icrt<8>(raw_out, crt_all, c, ic, b, e, batch, st);
-    else if (ic.W <= 20) launch_icrt<20>(raw_out, crt_all, c, ic, b, e, batch, st);
-    else if (ic.W <= 36) launch_icrt<36>(raw_out, crt_all, c, ic, b, e, batch, st);
-    else if (ic.W <= 52) launch_icrt<52>(raw_out, crt_all, c, ic, b, e, batch, st);
-    else if (ic.W <= 104) launch_icrt<104>(raw_out, crt_all, c, ic, b, e, batch, st);
-    else throw ArgError{"coefficient modulus wider than 104 words"};
-    CK(cudaGetLastError());
+    do_icrt_strided(c, raw_out, crt_all, lvl, b, e, batch, c->par.crtLen, st);
 }
 // CRT of `batch` polynomials: raw u32[batch][H][W] -> dst u32[batch][rows][H]
 static void do_crt(cuhe_ctx* c, uint32_t* dst, const uint32_t* raw, int lvl, int batch, cudaStream_t st) {
@@ -905,6 +911,19 @@ int cuhe_icrt_batch(cuhe_ctx* c, uint32_t* raw_out, const uint32_t* crt_all, int
         REQUIRE(batch >= 0 && batch <= 65535, "batch too large");
         DeviceGuard dg(c->device);
         do_icrt(c, raw_out, crt_all, lvl, b, e, batch, (cudaStream_t)stream);
+    });
+}
+
+int cuhe_icrt_slice_batch(cuhe_ctx* c, uint32_t* raw_slice_out, const uint32_t* crt_slice, int lvl, int coef_offset,
+                          int slice_len, int batch, cuhe_stream stream) {
+    return guarded([&] {
+        check_lvl(c, lvl); REQUIRE(raw_slice_out && crt_slice, "null pointer");
+        REQUIRE(coef_offset >= 0 && slice_len >= 1 && coef_offset + slice_len <= c->par.crtLen, "slice out of bounds");
+        REQUIRE(batch >= 0 && batch <= 65535, "batch too large");
+        DeviceGuard dg(c->device);
+        int e = c->par.modLen - coef_offset;          // coefficients >= modLen are not written
+        if (e > slice_len) e = slice_len;
+        do_icrt_strided(c, raw_slice_out, crt_slice, lvl, 0, e, batch, slice_len, (cudaStream_t)stream);
     });
 }
 

@@ -5,8 +5,10 @@ ciphertexts per device).  Here the CRT-residue axis is sharded: rank r of G owns
 primes r, r+G, r+2G, ... (so every level stays balanced while modSwitch drops
 the last prime).  Collectives appear only where the algorithm exchanges data:
 
-  * all-gather of cRep before ICRT (cuhe/CuHE.cu:366-382 needs every residue),
-    ICRT split by coefficient range, all-gather of the RAW slices;
+  * exchange of cRep before ICRT (cuhe/CuHE.cu:366-382 needs every residue of a coefficient):
+    ICRT is split by coefficient range, so an all-to-all delivers to rank j just slice j of every
+    residue (`exchange_for_icrt`; `all_gather_residues` is the simple all-gather form), then the
+    RAW slices are all-gathered;
   * broadcast of the dropped residue row in modSwitch (cuhe/Base.cu:1112-1138).
 
 The index arithmetic is pure torch (CPU or CUDA tensors) so it is tested on CPU
@@ -46,6 +48,34 @@ def all_gather_residues(local: torch.Tensor, L: int, world: int, group=None) -> 
     # gathered[r, b, i, :] is prime r + world*i
     full = gathered.permute(1, 2, 0, 3).reshape(B, rows_pad * world, H)
     return full[:, :L].contiguous()
+
+
+def exchange_for_icrt(local: torch.Tensor, L: int, rank: int, world: int, group=None) -> torch.Tensor:
+    """All-to-all form of the exchange before ICRT.  ICRT on rank j only needs the coefficient slice
+    [j*H/G, (j+1)*H/G) of every residue, so each rank sends slice j of its own rows to rank j
+    (bytes received per rank = 1/G of what the all-gather moves).
+    local: [batch][rows_pad][H]  ->  [batch][L][H/G] in prime order (this rank's coefficient slice)."""
+    B, rows_pad, H = local.shape
+    if world == 1:
+        return local[:, :L].contiguous()
+    assert H % world == 0
+    Hs = H // world
+    # send[j] = slice j of my rows: [world][B][rows_pad][Hs]
+    send = local.view(B, rows_pad, world, Hs).permute(2, 0, 1, 3).contiguous()
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv.view(world * B, rows_pad, Hs), send.view(world * B, rows_pad, Hs), group=group)
+    # recv[r, b, i, :] = prime r + world*i, my slice
+    return recv.permute(1, 2, 0, 3).reshape(B, rows_pad * world, Hs)[:, :L].contiguous()
+
+
+def all_gather_raw_slices(mine: torch.Tensor, world: int, group=None) -> torch.Tensor:
+    """mine: [batch][H/G][W] = this rank's coefficient slice of the RAW result -> [batch][H][W]."""
+    if world == 1:
+        return mine
+    B, Hs, W = mine.shape
+    gathered = torch.empty((world * B, Hs, W), dtype=mine.dtype, device=mine.device)
+    dist.all_gather_into_tensor(gathered, mine.contiguous(), group=group)
+    return gathered.view(world, B, Hs, W).permute(1, 0, 2, 3).reshape(B, world * Hs, W).contiguous()
 
 
 def coefficient_slice(H: int, rank: int, world: int) -> Tuple[int, int]:

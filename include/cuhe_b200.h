@@ -179,6 +179,13 @@ int cuhe_mul_crt_batch(cuhe_ctx* ctx, uint32_t* dst_crt, const uint32_t* a_raw, 
 int cuhe_icrt_batch(cuhe_ctx* ctx, uint32_t* raw_out, const uint32_t* crt_all, int lvl, int coef_begin, int coef_end,
                     int batch, cuhe_stream stream);
 
+/* icrt() on a coefficient SLICE (residue-sharded runs after an all-to-all): crt_slice
+ * u32[batch][numCrtPrime(lvl)][slice_len] holds coefficients [coef_offset, coef_offset+slice_len)
+ * of every residue; raw_slice_out u32[batch][slice_len][words(lvl)] receives the same coefficients
+ * (those >= modLen are left untouched, as in icrt()). */
+int cuhe_icrt_slice_batch(cuhe_ctx* ctx, uint32_t* raw_slice_out, const uint32_t* crt_slice, int lvl, int coef_offset,
+                          int slice_len, int batch, cuhe_stream stream);
+
 /* ---- device mod-P primitives on arrays: what tests/test_ModP.cu:57-137 drives
  *      (_add/_sub/_mul/_ls_modP of cuhe/ModP.h:68-289).  op: 0 add, 1 sub, 2 mul,
  *      3 shift-left by `shift` bits (0 <= shift < 192).  out[i] = x[i] op y[i].

@@ -55,6 +55,15 @@ def _worker(rank, world, port, q):
             raw_part[i, b:e] = o.icrt(got[i], lvl)[b:e]
         raw_all = sh.all_gather_raw(torch.from_numpy(raw_part.view(np.int32)), rank, world).numpy().view(np.uint32)
         assert np.array_equal(raw_all, raws), "RAW all-gather does not restore the polynomials"
+        # all-to-all form: each rank receives only its coefficient slice of every residue
+        Hs = H // world
+        sl = sh.exchange_for_icrt(t, L, rank, world).numpy().view(np.uint32)
+        assert sl.shape == (B, L, Hs) and np.array_equal(sl, full[:, :, rank * Hs:(rank + 1) * Hs])
+        raw_sl = np.zeros((B, Hs, W), dtype=np.uint32)
+        for i in range(B):
+            raw_sl[i] = o.icrt(got[i], lvl)[rank * Hs:(rank + 1) * Hs]
+        raw_all2 = sh.all_gather_raw_slices(torch.from_numpy(raw_sl.view(np.int32)), world).numpy().view(np.uint32)
+        assert np.array_equal(raw_all2, raws)
         # modswitch: owner of the last prime broadcasts its row
         owner, row = sh.owner_of(L - 1, world)
         assert owner == (L - 1) % world and sh.local_primes(L, owner, world)[row] == L - 1

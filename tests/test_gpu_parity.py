@@ -365,6 +365,14 @@ def test_sharded_contexts_match_unsharded(lib):
         shards[1].call("cuhe_icrt", p(raw), p(d_all), lvl, H // 2, H, shards[1].st())
         shards[0].torch.cuda.synchronize()
         assert np.array_equal(Eng.dn(raw, np.uint32), o.icrt(want, lvl))
+        # sliced ICRT (the all-to-all form): each "rank" holds only its coefficient slice of every residue
+        Hs = H // 2
+        for r, e in enumerate(shards):
+            sl = np.ascontiguousarray(gathered[None, :, r * Hs:(r + 1) * Hs])            # [1][L][Hs]
+            raw_sl = e.empty((1, Hs, W), np.uint32)
+            e.call("cuhe_icrt_slice_batch", p(raw_sl), p(e.up(sl)), lvl, r * Hs, Hs, 1, e.st())
+            want_sl = o.icrt(want, lvl)[r * Hs:(r + 1) * Hs]
+            assert np.array_equal(Eng.dn(raw_sl, np.uint32)[0], want_sl)
         # modswitch with the dropped row supplied by its owner
         last_owner = (L - 1) % 2
         d_last = shards[0].up(want[L - 1])
