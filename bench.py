@@ -318,7 +318,7 @@ def run_ours(args):
         tt = torch.tensor([el], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": B * args.steps / float(tt.item()), "unit": "mul/s", "h2d_bytes_per_step": int(2 * B * H * W * 4) * world,
-               "d2h_bytes_per_step": int(B * H * W * 4), "api": "pinned host RAW -> sharded cuhe_mul_crt_batch/all-gather/cuhe_icrt_batch -> host"}
+               "d2h_bytes_per_step": int(B * H * W * 4), "api": "pinned host RAW (replicated to every rank) -> sharded cuhe_mul_crt_batch / all-to-all / cuhe_icrt_slice_batch / all-gather -> host on rank 0"}
     if world == 1:
         # one e2e step = one call with Be = 4*B products from pinned host memory; the library pipelines
         # H2D | kernels | D2H over chunks of 8 products inside the call
