@@ -252,17 +252,29 @@ void orc_crt_add_nx1(uint32_t *x, const uint32_t *a, const uint32_t *scalar, int
 /* ---- Barrett: cuhe/Operations.cu:460-501 step order, kernels
  * cuhe/Base.cu:927-1001.  f: u32[L][N] (INTT result, deg <= 2n-2)
  * -> dst: u32[L][H].  u_ntt, m_ntt: u64[L][N]; m_crt: u32[L][H]. ----------- */
+static void barrett_rows(uint32_t *dst, const uint32_t *f, int rows, int L, int N, int H, int n,
+                         const uint32_t *primes, const uint64_t *u_ntt,
+                         const uint64_t *m_ntt, const uint32_t *m_crt,
+                         const uint64_t *roots);
 void orc_barrett(uint32_t *dst, const uint32_t *f, int L, int N, int H, int n,
                  const uint32_t *primes, const uint64_t *u_ntt,
                  const uint64_t *m_ntt, const uint32_t *m_crt,
                  const uint64_t *roots) {
+    barrett_rows(dst, f, L, L, N, H, n, primes, u_ntt, m_ntt, m_crt, roots);
+}
+/* rows = batch * L residue rows; row r uses prime r % L */
+static void barrett_rows(uint32_t *dst, const uint32_t *f, int rows, int L, int N, int H, int n,
+                         const uint32_t *primes, const uint64_t *u_ntt,
+                         const uint64_t *m_ntt, const uint32_t *m_crt,
+                         const uint64_t *roots) {
 #pragma omp parallel for schedule(dynamic)
-    for (int l = 0; l < L; l++) {
+    for (int row = 0; row < rows; row++) {
+        const int l = row % L;
         uint32_t p = primes[l];
         uint32_t *src = (uint32_t *)malloc(sizeof(uint32_t) * N);
         uint32_t *crt = (uint32_t *)malloc(sizeof(uint32_t) * N);
         uint64_t *nt = (uint64_t *)malloc(sizeof(uint64_t) * N);
-        memcpy(src, f + (size_t)l * N, sizeof(uint32_t) * N);
+        memcpy(src, f + (size_t)row * N, sizeof(uint32_t) * N);
         /* ntt of f>>(n-1): reads H words starting at n-1 (Operations.cu:470-471) */
         orc_ntt_ext(nt, src + n - 1, N, roots);
         for (int i = 0; i < N; i++) nt[i] = mulP(nt[i], u_ntt[(size_t)l * N + i]);
@@ -288,7 +300,7 @@ void orc_barrett(uint32_t *dst, const uint32_t *f, int L, int N, int H, int n,
                 src[i] = d - s;
             }
         }
-        memcpy(dst + (size_t)l * H, src, sizeof(uint32_t) * H);
+        memcpy(dst + (size_t)row * H, src, sizeof(uint32_t) * H);
         free(src); free(crt); free(nt);
     }
 }
@@ -355,6 +367,39 @@ void orc_mul_raw_to_crt(uint32_t *dst, const uint32_t *a_raw, const uint32_t *b_
     }
     orc_barrett(dst, hold, L, N, H, n, primes, u_ntt, m_ntt, m_crt, roots);
     free(ca); free(cb); free(hold);
+}
+
+/* `batch` independent products, every (polynomial, residue) pair an OpenMP task: the CPU arm of
+ * bench.py (all host threads busy even when the level has fewer primes than cores).
+ * a,b: u32[batch][H][W] -> dst_raw u32[batch][H][W] (CRT, NTT, mul, INTT, Barrett, ICRT) */
+void orc_mul_raw_batch(uint32_t *dst_raw, const uint32_t *a_raw, const uint32_t *b_raw, int batch,
+                       int L, int W, int Wp, int N, int H, int n, const uint32_t *primes,
+                       const uint64_t *u_ntt, const uint64_t *m_ntt, const uint32_t *m_crt,
+                       const uint64_t *roots, const uint32_t *M, const uint32_t *mi, const uint32_t *bi) {
+    const size_t rows = (size_t)batch * L;
+    uint32_t *ca = (uint32_t *)calloc(rows * H, 4);
+    uint32_t *cb = (uint32_t *)calloc(rows * H, 4);
+    uint32_t *hold = (uint32_t *)malloc(sizeof(uint32_t) * rows * N);
+    uint32_t *cr = (uint32_t *)malloc(sizeof(uint32_t) * rows * H);
+    for (int b = 0; b < batch; b++) {
+        orc_crt(ca + (size_t)b * L * H, a_raw + (size_t)b * H * W, L, W, n, H, primes);
+        orc_crt(cb + (size_t)b * L * H, b_raw + (size_t)b * H * W, L, W, n, H, primes);
+    }
+#pragma omp parallel for schedule(dynamic)
+    for (long r = 0; r < (long)rows; r++) {
+        uint64_t *A = (uint64_t *)malloc(sizeof(uint64_t) * N);
+        uint64_t *B = (uint64_t *)malloc(sizeof(uint64_t) * N);
+        orc_ntt_ext(A, ca + (size_t)r * H, N, roots);
+        orc_ntt_ext(B, cb + (size_t)r * H, N, roots);
+        for (int i = 0; i < N; i++) A[i] = mulP(A[i], B[i]);
+        orc_intt_modp(hold + (size_t)r * N, A, N, roots, primes[r % L]);
+        free(A); free(B);
+    }
+    barrett_rows(cr, hold, (int)rows, L, N, H, n, primes, u_ntt, m_ntt, m_crt, roots);
+    memset(dst_raw, 0, sizeof(uint32_t) * (size_t)batch * H * W);
+    for (int b = 0; b < batch; b++)
+        orc_icrt(dst_raw + (size_t)b * H * W, cr + (size_t)b * L * H, L, W, Wp, n, H, primes, M, mi, bi);
+    free(ca); free(cb); free(hold); free(cr);
 }
 
 int orc_max_threads(void) {

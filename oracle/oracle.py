@@ -306,6 +306,22 @@ class Oracle:
             _p(_roots(self.N)))
         return out
 
+    def mul_raw_batch(self, a_raw: np.ndarray, b_raw: np.ndarray, lvl: int) -> np.ndarray:
+        """batch of products RAW -> RAW with every (polynomial, residue) pair an OpenMP task
+        (the CPU arm of bench.py).  a_raw, b_raw: u32[batch][H][W]"""
+        t = self.barrett_tables()
+        L, W, Wp = self.L(lvl), self.W(lvl), self.W(lvl + 1)
+        ic = self.icrt_const(lvl)
+        a_raw = np.ascontiguousarray(a_raw, dtype=np.uint32)
+        b_raw = np.ascontiguousarray(b_raw, dtype=np.uint32)
+        batch = a_raw.shape[0]
+        out = np.zeros_like(a_raw)
+        lib().orc_mul_raw_batch(
+            _p(out), _p(a_raw), _p(b_raw), C.c_int(batch), C.c_int(L), C.c_int(W), C.c_int(Wp), C.c_int(self.N),
+            C.c_int(self.H), C.c_int(self.n), _p(self.primes_np), _p(t["u_ntt"]), _p(t["m_ntt"]), _p(t["m_crt"]),
+            _p(_roots(self.N)), _p(ic.q), _p(np.ascontiguousarray(ic.qp)), _p(ic.qpinv))
+        return out
+
     def mul_exact(self, a: Sequence[int], b: Sequence[int], lvl: int) -> List[int]:
         """(a*b mod Phi_m) mod q_lvl with big ints / GMP -- the NTL host path
         of examples/DHS/DHS.cu:219-221."""
