@@ -45,6 +45,12 @@ SYMBOLS = {
     "cuhe_malloc": (_i, [_vp, C.POINTER(_vp), C.c_size_t, _vp]),
     "cuhe_free": (_i, [_vp, _vp, _vp]),
     "cuhe_pool_trim": (_i, [_vp]),
+    "cuhe_memcpy": (_i, [_vp, _vp, _vp, C.c_size_t, _i, _vp]),
+    "cuhe_memset": (_i, [_vp, _vp, _i, C.c_size_t, _vp]),
+    "cuhe_stream_sync": (_i, [_vp, _vp]),
+    "cuhe_host_alloc": (_i, [C.POINTER(_vp), C.c_size_t]),
+    "cuhe_host_free": (_i, [_vp]),
+    "cuhe_device_count": (_i, []),
     "cuhe_crt": (_i, [_vp, _vp, _vp, _i, _vp]),
     "cuhe_icrt": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "cuhe_ntt": (_i, [_vp, _vp, _vp, _i, _vp]),

@@ -658,6 +658,36 @@ int cuhe_pool_trim(cuhe_ctx* c) {
     return guarded([&] { REQUIRE(c, "null context"); DeviceGuard dg(c->device); CK(cudaDeviceSynchronize()); CK(cudaMemPoolTrimTo(c->pool, 0)); });
 }
 
+int cuhe_memcpy(cuhe_ctx* c, void* dst, const void* src, size_t bytes, int kind, cuhe_stream stream) {
+    return guarded([&] {
+        REQUIRE(c && (bytes == 0 || (dst && src)), "null argument"); REQUIRE(kind >= 0 && kind <= 2, "bad copy kind");
+        DeviceGuard dg(c->device);
+        const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : (kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice);
+        if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, k, (cudaStream_t)stream));
+    });
+}
+int cuhe_memset(cuhe_ctx* c, void* ptr, int value, size_t bytes, cuhe_stream stream) {
+    return guarded([&] {
+        REQUIRE(c && (bytes == 0 || ptr), "null argument");
+        DeviceGuard dg(c->device);
+        if (bytes) CK(cudaMemsetAsync(ptr, value, bytes, (cudaStream_t)stream));
+    });
+}
+int cuhe_stream_sync(cuhe_ctx* c, cuhe_stream stream) {
+    return guarded([&] { REQUIRE(c, "null context"); DeviceGuard dg(c->device); CK(cudaStreamSynchronize((cudaStream_t)stream)); });
+}
+int cuhe_host_alloc(void** ptr, size_t bytes) {
+    return guarded([&] { REQUIRE(ptr, "null argument"); CK(cudaMallocHost(ptr, bytes ? bytes : 16)); });
+}
+int cuhe_host_free(void* ptr) {
+    return guarded([&] { if (ptr) CK(cudaFreeHost(ptr)); });
+}
+int cuhe_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
 int cuhe_crt(cuhe_ctx* c, uint32_t* dst, const uint32_t* raw, int lvl, cuhe_stream stream) {
     return guarded([&] {
         check_lvl(c, lvl); REQUIRE(dst && raw, "null pointer");

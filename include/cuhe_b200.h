@@ -88,6 +88,15 @@ int cuhe_ctx_set_poly_modulus_host(cuhe_ctx* ctx, const int64_t* coeffs_host, in
 int cuhe_malloc(cuhe_ctx* ctx, void** ptr, size_t bytes, cuhe_stream stream);
 int cuhe_free(cuhe_ctx* ctx, void* ptr, cuhe_stream stream);
 int cuhe_pool_trim(cuhe_ctx* ctx); /* stopAllocator: release cached blocks */
+/* copies / fills / synchronisation on the context's device, so a host layer (the CuHE.h shim, a C
+ * client) needs no CUDA headers of its own: the cudaMemcpyAsync / cudaMemsetAsync /
+ * cudaStreamSynchronize calls of cuhe/CuHE.cu:317-348,468-488.  kind: 0 H2D, 1 D2H, 2 D2D. */
+int cuhe_memcpy(cuhe_ctx* ctx, void* dst, const void* src, size_t bytes, int kind, cuhe_stream stream);
+int cuhe_memset(cuhe_ctx* ctx, void* ptr, int value, size_t bytes, cuhe_stream stream);
+int cuhe_stream_sync(cuhe_ctx* ctx, cuhe_stream stream);
+int cuhe_host_alloc(void** ptr, size_t bytes);   /* pinned staging buffer (dhBuffer_, cuhe/CuHE.cu:34-40) */
+int cuhe_host_free(void* ptr);
+int cuhe_device_count(void);
 
 /* ---- domain conversions ---------------------------------------------------- */
 /* crt(): cuhe/Operations.cu:245-253, kernel cuhe/Base.cu:857-879.

@@ -104,3 +104,42 @@ def test_plain_c_client_gpu_mode(lib):
     r = subprocess.run([exe, "gpu"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "gpu ok" in r.stdout
+
+
+def _build_cpp_compat_test():
+    import subprocess
+    libdir = os.path.join(ROOT, "cuhe_b200")
+    if not os.path.exists(os.path.join(libdir, "libcuhe_compat.so")):
+        import __graft_entry__ as ge
+        ge.build()
+    out = os.path.join(ROOT, "tests", "_compat_test")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(libdir, "host"),
+                           "-I", "/usr/local/cuda/include", "-o", out,
+                           os.path.join(ROOT, "tests", "cpp", "compat_test.cpp"),
+                           "-L", libdir, "-lcuhe_compat", "-lcuhe_b200", f"-Wl,-rpath,{libdir}"])
+    return out
+
+
+def test_cpp_host_layer_builds_and_exports_the_reference_interface(lib):
+    """cuhe_b200/host: the C++ layer with the reference's names (namespace cuHE) compiles with plain
+    g++ (no NTL, no nvcc) and a client written against that interface links."""
+    import subprocess
+    _build_cpp_compat_test()
+    syms = subprocess.run(["nm", "-DC", os.path.join(ROOT, "cuhe_b200", "libcuhe_compat.so")],
+                          capture_output=True, text=True).stdout
+    for name in ("cuHE::setParameters(int, int, int, int, int, int)", "cuHE::initCuHE(", "cuHE::mulZZX(",
+                 "cuHE::cAnd(cuHE::CuCtxt&, cuHE::CuCtxt&, cuHE::CuCtxt&", "cuHE::cAnd(cuHE::CuCtxt&, cuHE::CuCtxt&, cuHE::CuPtxt&",
+                 "cuHE::cXor(", "cuHE::cNot(", "cuHE::copy(cuHE::CuCtxt&, cuHE::CuCtxt", "cuHE::moveTo(", "cuHE::copyTo(",
+                 "cuHE::CuCtxt::relin(", "cuHE::CuCtxt::modSwitch(", "cuHE::CuPolynomial::x2n(", "cuHE::initRelinearization(",
+                 "cuHE::multiGPUs(int)", "cuHE::numGPUs()", "cuHE::startAllocator()", "cuHE::stopAllocator()", "cuHE::param"):
+        assert name in syms, name
+
+
+@pytest.mark.gpu
+def test_cpp_client_of_the_reference_interface(lib):
+    """tests/cpp/compat_test.cpp: simple_DHS-style call sequences through the C++ host layer,
+    checked against exact host big-integer arithmetic."""
+    import subprocess
+    exe = _build_cpp_compat_test()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "compat ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
