@@ -129,9 +129,14 @@ CuPolynomial::CuPolynomial()
     : logq_(-1), domain_(-1), device_(-1), isProd_(false), zRepPtr_(nullptr), rRep_(nullptr), cRep_(nullptr), nRep_(nullptr),
       owns_(true) {}
 CuPolynomial::~CuPolynomial() {
+    // may legitimately run twice on the same storage (explicit call + scope exit, as the reference's
+    // examples do); every pointer is nulled through a volatile access so the second run is a no-op
     reset();
     delete zRepPtr_;
-    zRepPtr_ = nullptr;
+    *const_cast<ZZX* volatile*>(&zRepPtr_) = nullptr;
+    *const_cast<uint32* volatile*>(&rRep_) = nullptr;
+    *const_cast<uint32* volatile*>(&cRep_) = nullptr;
+    *const_cast<uint64* volatile*>(&nRep_) = nullptr;
 }
 ZZX& CuPolynomial::zRepRef() {
     if (!zRepPtr_) zRepPtr_ = new ZZX();

@@ -3,9 +3,12 @@
 // Mirrors the call sequences of examples/DHS/simple_DHS.cu and cuhe/CuHE.cu:259-268 (mulZZX) and
 // checks results with exact big-integer arithmetic done independently on the host (zz_lite).
 // Prints "compat ok" and exits 0 on success.
+#include <csignal>
 #include <cstdio>
 #include <cstdlib>
+#include <execinfo.h>
 #include <new>
+#include <unistd.h>
 #include <vector>
 
 #include "cuhe_compat.hpp"
@@ -38,12 +41,25 @@ static ZZX mul_mod_ref(const ZZX& a, const ZZX& b, int m, const ZZ& q) {
     return r;
 }
 
+static void on_crash(int sig) {
+    void* bt[64];
+    int n = backtrace(bt, 64);
+    dprintf(2, "signal %d, backtrace:\n", sig);
+    backtrace_symbols_fd(bt, n, 2);
+    _exit(3);
+}
+#define STEP(msg) do { std::printf("step: %s\n", msg); std::fflush(stdout); } while (0)
+
 int main() {
+    std::signal(SIGSEGV, on_crash);
+    std::signal(SIGABRT, on_crash);
+    std::setvbuf(stdout, nullptr, _IONBF, 0);
     unsigned seed = 12345;
     // ---- simple_DHS.cu:218 parameters: CuDHS(5, 2, 1, 61, 20, 8191) -----------------------------
     setParameters(5, 2, 1, 61, 20, 8191);
     EXPECT(param.modLen == 8190 && param.nttLen == 16384 && param.numCrtPrime == 7 && param.numEvalKey == 141);
     EXPECT(param._numCrtPrime(1) == 6 && param._wordsCoeff(0) == 5 && param._getLevel(param._logCoeff(2)) == 2);
+    STEP("parameters");
     multiGPUs(1);
     EXPECT(numGPUs() == 1);
     const int n = param.modLen, m = param.mSize;
@@ -51,6 +67,7 @@ int main() {
     for (int i = 0; i <= n; i++) SetCoeff(phi, i, 1);
     std::vector<ZZ> coeffMod((size_t)param.depth);
     initCuHE(coeffMod.data(), phi);
+    STEP("initCuHE");
     EXPECT(NumBits(coeffMod[0]) == 141);
     for (int i = 1; i < param.depth; i++) EXPECT(coeffMod[(size_t)i] < coeffMod[(size_t)i - 1]);
     const ZZ q0 = coeffMod[0], q1 = coeffMod[1];
@@ -61,6 +78,7 @@ int main() {
     ZZX one; SetCoeff(one, 0, 1);
     ZZX out;
     mulZZX(out, one, b, 0, 0);
+    STEP("mulZZX 1*b");
     EXPECT(out == b);
     ZZX sparse;
     SetCoeff(sparse, 0, rand_below(q0, seed)); SetCoeff(sparse, 17, rand_below(q0, seed));
@@ -73,6 +91,7 @@ int main() {
     for (long i = 0; i <= deg(sparse); i++) SetCoeff(s1, i, coeff(sparse, i) % q1);
     mulZZX(out, s1, b1, 1, 0);
     EXPECT(out == mul_mod_ref(s1, b1, m, q1));
+    STEP("mulZZX vs exact");
 
     // ---- CuCtxt domain machine, cXor / cNot / copy / modSwitch ---------------------------------------
     {
@@ -87,12 +106,14 @@ int main() {
         ca.x2c();
         cb.x2c();
         cXor(cx, ca, cb);
+        STEP("cXor");
         CuCtxt cy;
         copy(cy, cx);                                   // source by value: must neither alias nor double free
         cx.x2z();
         ZZX sum;
         for (int i = 0; i < n; i++) SetCoeff(sum, i, (coeff(b, i) + coeff(sparse, i)) % q0);
         EXPECT(cx.zRep() == sum);
+        STEP("copy");
         cNot(cy, cy);
         cy.x2z();
         ZZX nsum = sum;
@@ -111,8 +132,10 @@ int main() {
         cb.x2z();
         EXPECT(deg(cb.zRep()) < n);
         for (long i = 0; i <= deg(cb.zRep()); i++) EXPECT(coeff(cb.zRep(), i) < q1);
+        STEP("modSwitch");
         cb.~CuCtxt();                                   // explicit destructor, then the implicit one (Prince.cu:298-318)
     }
+    STEP("scope exit after explicit destructor");
 
     // ---- relinearization plumbing (values are checked bit-for-bit by tests/test_gpu_api.py) ------------
     resetParameters();
@@ -122,6 +145,7 @@ int main() {
     std::vector<ZZX> ek((size_t)param.numEvalKey);
     for (auto& e : ek) for (int i = 0; i < n; i++) SetCoeff(e, i, rand_below(cm2[0], seed));
     initRelinearization(ek.data());
+    STEP("initRelinearization");
     {
         ZZX a2, b2;
         for (int i = 0; i < n; i++) { SetCoeff(a2, i, rand_below(cm2[0], seed)); SetCoeff(b2, i, rand_below(cm2[0], seed)); }
@@ -136,6 +160,7 @@ int main() {
         x.x2z();
         EXPECT(deg(x.zRep()) < n);
     }
+    STEP("relin");
     resetParameters();
     if (fails == 0) std::printf("compat ok\n");
     return fails ? 1 : 0;
