@@ -458,3 +458,64 @@ def test_fused_cluster_ntt_matches(lib, monkeypatch):
         assert np.array_equal(res, o.icrt(o.mul_raw_to_crt(ra, rb, 0), 0))
     finally:
         e.close()
+
+
+def _relin_rows_oracle(o, eks, raw, rows):
+    """Oracle key switch (cuhe/Relinearization.cu:76-88) for a subset of residue rows at level 0:
+    sum_k NTT(digit_k) * NTT(ek_k mod p_l).  Only the listed rows' keys are transformed."""
+    from oracle import oracle as orc
+    N, K0 = o.N, o.par.numEvalKey
+    rows = list(rows)
+    acc = {l: np.zeros(N, dtype=np.uint64) for l in rows}
+    for k in range(K0):
+        D = orc.ntt_ext(o.digits(raw, 0, k), N)
+        ek = orc.ntt_ext(o.crt(eks[k], 0)[rows], N)
+        for i, l in enumerate(rows):
+            acc[l] = orc.ntt_add(acc[l], orc.ntt_mul(D, ek[i]))
+    return acc
+
+
+def test_config3_relin_full_size(lib):
+    """BASELINE configs[2]: key switch at N=65536, 44 primes, 66 evaluation keys (1.52 GB of keys
+    resident in HBM).  Full-size parity on the first and last residue rows at level 0 (the oracle
+    transforms only those rows' keys; every row goes through the same kernel)."""
+    ps = (44, 2, 16, 24, 24, 32767)
+    e = Eng(lib, ps)
+    try:
+        o = e.orc
+        K0, W0, H, N, L0 = o.par.numEvalKey, o.W(0), o.H, o.N, o.L0
+        assert (N, L0, K0) == (65536, 44, 66)
+        rng = np.random.default_rng(5)
+        eks = rng.integers(0, 1 << 32, size=(K0, H, W0), dtype=np.uint32)
+        eks[:, o.n:, :] = 0
+        eks[:, :, W0 - 1] = 0                           # keep every coefficient below q0 (33 words, 1056 bits)
+        e.call("cuhe_relin_init", p(e.up(eks)), e.st())
+        raw = rng.integers(0, 1 << 32, size=(H, W0), dtype=np.uint32)
+        raw[o.n:] = 0
+        raw[:, W0 - 1] = 0
+        d_out = e.empty((L0, N), np.uint64)
+        e.call("cuhe_relin", p(d_out), p(e.up(raw)), 0, e.st())
+        got = Eng.dn(d_out, np.uint64)
+        want = _relin_rows_oracle(o, eks, raw, (0, L0 - 1))
+        for l, acc in want.items():
+            assert np.array_equal(got[l], acc), f"relin row {l} (prime {o.primes[l]})"
+    finally:
+        e.close()
+
+
+@pytest.mark.parametrize("ps", [(64, 2, 16, 24, 24, 32767), (25, 2, 16, 25, 25, 21845)],
+                         ids=["config5_64primes_1536bit", "prince_32k_25primes"])
+def test_large_prime_counts_mul(lib, ps):
+    """BASELINE configs[4] (64 primes, ~1536-bit modulus) and the Prince parameter set (N=32768, 25
+    primes): whole multiply RAW -> RAW against the oracle."""
+    e = Eng(lib, ps)
+    try:
+        o = e.orc
+        _, ra = rand_poly_raw(o, 0, 61)
+        _, rb = rand_poly_raw(o, 0, 62)
+        out = np.zeros_like(ra)
+        e.call("cuhe_mul_raw_host", out.ctypes.data_as(C.c_void_p), ra.ctypes.data_as(C.c_void_p),
+               rb.ctypes.data_as(C.c_void_p), 0, e.st())
+        assert np.array_equal(out, o.icrt(o.mul_raw_to_crt(ra, rb, 0), 0))
+    finally:
+        e.close()
