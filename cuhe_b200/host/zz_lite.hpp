@@ -9,6 +9,8 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
+#include <istream>
+#include <ostream>
 #include <string>
 #include <vector>
 
@@ -149,6 +151,46 @@ private:
         return r;
     }
 };
+
+// decimal text (NTL: operator<<, conv<ZZ>(const char*))
+inline std::string to_decimal(const ZZ& a) {
+    if (a.is_zero()) return "0";
+    std::vector<uint32_t> mag = a.limbs();
+    std::string digits;
+    while (!mag.empty()) {                                   // divide by 10^9, collect remainders
+        uint64_t rem = 0;
+        for (size_t i = mag.size(); i-- > 0;) {
+            const uint64_t cur = (rem << 32) | mag[i];
+            mag[i] = (uint32_t)(cur / 1000000000u);
+            rem = cur % 1000000000u;
+        }
+        while (!mag.empty() && mag.back() == 0) mag.pop_back();
+        for (int k = 0; k < 9; k++) {
+            digits.push_back((char)('0' + rem % 10));
+            rem /= 10;
+            if (mag.empty() && rem == 0) break;
+        }
+    }
+    if (a.negative()) digits.push_back('-');
+    return std::string(digits.rbegin(), digits.rend());
+}
+inline ZZ from_decimal(const char* s) {
+    while (*s == ' ' || *s == '\t' || *s == '\n' || *s == '\r') s++;
+    bool neg = false;
+    if (*s == '-' || *s == '+') { neg = (*s == '-'); s++; }
+    ZZ r;
+    const ZZ ten9(1000000000L);
+    while (*s >= '0' && *s <= '9') {
+        long chunk = 0, scale = 1;
+        for (int k = 0; k < 9 && *s >= '0' && *s <= '9'; k++, s++) { chunk = chunk * 10 + (*s - '0'); scale *= 10; }
+        r = r * (scale == 1000000000L ? ten9 : ZZ(scale)) + ZZ(chunk);
+    }
+    return neg ? -r : r;
+}
+inline std::ostream& operator<<(std::ostream& os, const ZZ& a) { return os << to_decimal(a); }
+inline std::istream& operator>>(std::istream& is, ZZ& a) { std::string t; is >> t; a = from_decimal(t.c_str()); return is; }
+template <class T> T conv(const char* s);
+template <> inline ZZ conv<ZZ>(const char* s) { return from_decimal(s); }
 
 inline ZZ to_ZZ(long v) { return ZZ(v); }
 inline long to_long(const ZZ& a) { return a.to_long(); }

@@ -57,6 +57,32 @@ def poly_inverse_mod(f: List[int], phi: List[int], p: int) -> List[int]:
     raise ArithmeticError("polynomial is not invertible")
 
 
+def _inverse_job(args):
+    f, phi, p = args
+    try:
+        return poly_inverse_mod(f, phi, p)
+    except ArithmeticError:
+        return None
+
+
+def poly_inverse_all(f: List[int], phi: List[int], primes: List[int]) -> List[List[int]]:
+    """f^-1 modulo every CRT prime; the primes are independent, so large rings (Prince: n = 16384,
+    25 primes, ~4 s each) are spread over host processes."""
+    jobs = [(f, phi, p) for p in primes]
+    if len(phi) < 10000 or len(primes) < 4:
+        res = [_inverse_job(j) for j in jobs]
+    else:
+        import multiprocessing as mp
+        import os
+        from concurrent.futures import ProcessPoolExecutor
+        workers = min(len(primes), max(1, (os.cpu_count() or 2) - 1))
+        with ProcessPoolExecutor(max_workers=workers, mp_context=mp.get_context("spawn")) as ex:
+            res = list(ex.map(_inverse_job, jobs))
+    if any(r is None for r in res):
+        raise ArithmeticError("polynomial is not invertible")
+    return res
+
+
 def crt_combine(residues: List[List[int]], primes: List[int]) -> List[int]:
     q = 1
     for p in primes:
@@ -108,7 +134,7 @@ class DHS:
             f = [p * c for c in ft]
             f[0] += 1
             try:
-                invs = [poly_inverse_mod(f, self.phi, pr) for pr in self.primes[:L0]]
+                invs = poly_inverse_all(f, self.phi, self.primes[:L0])
                 break
             except ArithmeticError:
                 continue

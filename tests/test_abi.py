@@ -106,18 +106,27 @@ def test_plain_c_client_gpu_mode(lib):
     assert "gpu ok" in r.stdout
 
 
-def _build_cpp_compat_test():
+def _build_cpp_compat_test(name="compat_test"):
     import subprocess
     libdir = os.path.join(ROOT, "cuhe_b200")
     if not os.path.exists(os.path.join(libdir, "libcuhe_compat.so")):
         import __graft_entry__ as ge
         ge.build()
-    out = os.path.join(ROOT, "tests", "_compat_test")
+    out = os.path.join(ROOT, "tests", "_" + name)
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(libdir, "host"),
                            "-I", "/usr/local/cuda/include", "-o", out,
-                           os.path.join(ROOT, "tests", "cpp", "compat_test.cpp"),
+                           os.path.join(ROOT, "tests", "cpp", name + ".cpp"),
                            "-L", libdir, "-lcuhe_compat", "-lcuhe_b200", f"-Wl,-rpath,{libdir}"])
     return out
+
+
+def test_cpp_key_text_format(lib):
+    """cuHE_Utils::Picklable / PicklableMap (cuhe/Utils.h:39-93), the key/polynomial text format of
+    examples/DHS/DHS.cu:57-189 -- pure host code, runs without a GPU."""
+    import subprocess
+    exe = _build_cpp_compat_test("utils_test")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "utils ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 def test_cpp_host_layer_builds_and_exports_the_reference_interface(lib):
@@ -131,7 +140,8 @@ def test_cpp_host_layer_builds_and_exports_the_reference_interface(lib):
                  "cuHE::cAnd(cuHE::CuCtxt&, cuHE::CuCtxt&, cuHE::CuCtxt&", "cuHE::cAnd(cuHE::CuCtxt&, cuHE::CuCtxt&, cuHE::CuPtxt&",
                  "cuHE::cXor(", "cuHE::cNot(", "cuHE::copy(cuHE::CuCtxt&, cuHE::CuCtxt", "cuHE::moveTo(", "cuHE::copyTo(",
                  "cuHE::CuCtxt::relin(", "cuHE::CuCtxt::modSwitch(", "cuHE::CuPolynomial::x2n(", "cuHE::initRelinearization(",
-                 "cuHE::multiGPUs(int)", "cuHE::numGPUs()", "cuHE::startAllocator()", "cuHE::stopAllocator()", "cuHE::param"):
+                 "cuHE::multiGPUs(int)", "cuHE::numGPUs()", "cuHE::startAllocator()", "cuHE::stopAllocator()", "cuHE::param",
+                 "cuHE_Utils::Picklable::pickle", "cuHE_Utils::PicklableMap::toString", "cuHE_Utils::PicklableMap::get("):
         assert name in syms, name
 
 
@@ -143,3 +153,22 @@ def test_cpp_client_of_the_reference_interface(lib):
     exe = _build_cpp_compat_test()
     r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "compat ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_python_key_text_format_matches_cpp(lib):
+    """cuhe_b200/utils.py and the C++ twin agree on the text (same strings as tests/cpp/utils_test.cpp)."""
+    from cuhe_b200.utils import Picklable, PicklableMap
+    big = 1234567890123456789012345678901234567890123456789012345678901234567890
+    pk = Picklable.from_poly("pk0", [5, big, 0, 7, 0, 0])
+    assert pk.pickle() == f"pk0,5,{big},0,7" and pk.getCoeffsLen() == 4
+    d = Picklable("d", [24, 0, 0])
+    assert d.pickle() == "d,24,0,0" and d.getPoly() == [24]
+    semi = Picklable.parse("x;1;;2", ";")
+    assert semi.pickle() == "x;1;2"
+    m = PicklableMap([d, pk])
+    assert m.toString() == d.pickle() + "\n" + pk.pickle()
+    back = PicklableMap.parse(m.toString())
+    assert back.get("pk0").getPoly() == [5, big, 0, 7] and back.get("d").getValues() == "24"
+    with pytest.raises(KeyError):
+        back.get("nope")
+    assert PicklableMap.parse("a:1:2|b:3", "|", ":").toString() == "a:1:2|b:3"

@@ -1,0 +1,68 @@
+"""BASELINE configs[3] and the reference's only fixed known answer, on the GPU: homomorphic PRINCE
+over DHS at (25, 2, 16, 25, 25, 21845) -- N = 32768, 25 primes, 40 evaluation keys, 24 levels --
+through the cuHE interface (examples/Prince/Prince.cu:56-98).  1920 cAnd, 1152 relin and 2688
+modSwitch calls must leave ciphertexts that decrypt to 9fb51935fc3df524.
+
+Also the same S-box schedule cross-checked ciphertext-for-ciphertext against the CPU oracle engine
+(same keys, same randomness => identical ZZX outputs, not merely identical decryptions)."""
+import random
+import time
+
+import pytest
+
+import prince_he as ph
+from common import get_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu():
+    import torch
+    assert torch.cuda.is_available()
+    import cuhe_b200 as ch
+    return ch
+
+
+def test_sbox_ciphertexts_equal_oracle_engine():
+    from dhs_host import DHS
+    from oracle_engine import OracleEngine
+    ps = (5, 2, 16, 25, 25, 8191)
+    o = get_oracle(ps)
+    ch = _gpu()
+    try:
+        gpu = DHS(ch, *ps, phi=o.phi, seed=3)
+        cpu = DHS(OracleEngine(), *ps, phi=o.phi, seed=3)
+        assert gpu.pk[0] == cpu.pk[0] and gpu.sk[0] == cpu.sk[0]
+        rng = random.Random(9)
+        bits = [rng.randrange(2) for _ in range(4)]
+        cg = [gpu.encrypt([b], 0) for b in bits]
+        cc = [cpu.encrypt([b], 0) for b in bits]
+        assert cg == cc
+        og = ph.HomOps(ch, gpu)._sbox(cg, 0, ph.ANF_FWD)
+        oc = ph.HomOps(cpu.ch, cpu)._sbox(cc, 0, ph.ANF_FWD)
+        assert og == oc, "S-box output ciphertexts differ between the GPU path and the oracle"
+        v = ph.SBOX[int("".join(map(str, bits)), 2)]
+        assert [gpu.decrypt(x, 2)[0] for x in og] == [(v >> 3) & 1, (v >> 2) & 1, (v >> 1) & 1, v & 1]
+    finally:
+        ch.resetParameters()
+
+
+def test_homomorphic_prince_known_answer():
+    from dhs_host import DHS
+    ch = _gpu()
+    o = get_oracle(ph.PRINCE_PARAMS)
+    t0 = time.time()
+    try:
+        dhs = DHS(ch, *ph.PRINCE_PARAMS, phi=o.phi, seed=2026)
+        t_keys = time.time() - t0
+        ch.launch_count(reset=True)
+        t1 = time.time()
+        bits, ops = ph.hom_prince(ch, dhs, [0] * 64, [1] * 64, [0] * 64, check_rounds=(0, 11))
+        t_eval = time.time() - t1
+        print(f"\nkeygen {t_keys:.1f} s, encrypt+evaluate+decrypt {t_eval:.1f} s, ops {ops.counts}, "
+              f"kernel launches {ch.launch_count()}")
+        assert ops.counts == dict(cAnd=1920, relin=1152, modSwitch=2688, sbox=192)
+        assert ops.round_bits == ops.round_want
+        assert ph.bits_to_hex(bits) == ph.KAT_HEX
+    finally:
+        ch.resetParameters()
