@@ -11,8 +11,12 @@
  *
  * Parity status: pinned against big-integer arithmetic for the mod-P
  * primitives (tests/test_ModP.cu:57-137) and against the O(N^2) DFT for the
- * ext-NTT (tests/test_ntt.cu:38-64) in tests/test_oracle.py; the other
- * domains are unpinned by reference tests (the reference has none).
+ * ext-NTT (tests/test_ntt.cu:38-64) in tests/test_oracle.py, and end to end
+ * by the reference's only fixed known answer: homomorphic PRINCE run on this
+ * code decrypts to 9fb51935fc3df524 (examples/Prince/Prince.cu:96;
+ * tests/test_prince_circuit.py, log in tests/golden/prince_kat_oracle.log).
+ * Exact values of intermediate ciphertext words are not stored by any
+ * reference test; they rest on the literal restatement + exact ring arithmetic.
  *
  * Build: make -C oracle   (gcc -O3 -fopenmp -shared)
  */

@@ -12,10 +12,19 @@ headers, texture references rejected by nvcc 12.9), it stores no golden
 vectors and seeds everything with time(NULL); what its own tests pin is
   * tests/test_ModP.cu:57-137  -- mod-P primitives == big-int arithmetic mod P
   * tests/test_ntt.cu:38-64    -- ext-NTT == O(N^2) DFT with g, w0=g^(65536/N)
-  * examples/Prince/Prince.cu:96 -- the PRINCE known-answer (needs NTL; gated)
-Those properties are checked for this oracle in tests/test_oracle.py; the
-intermediate domains (CRT primes, ICRT constants, modswitch, Barrett) are
-"parity unpinned by reference tests" and rest on the literal restatement here.
+  * examples/Prince/Prince.cu:96,109-144 -- the only FIXED known answer: homomorphic PRINCE of
+    0^64 under k0 = 1^64, k1 = 0^64 decrypts to 9fb51935fc3df524 (+ 12 per-round states)
+The first two are checked for this oracle in tests/test_oracle.py.  The third is checked in
+tests/test_prince_circuit.py: the whole homomorphic PRINCE (1920 cAnd, 1152 relin, 2688 modSwitch,
+24 levels, real DHS keys at (25,2,16,25,25,21845)) run on THIS oracle behind the cuHE interface
+(tests/oracle_engine.py) decrypts to the reference's vector and round states -- log of the run in
+tests/golden/prince_kat_oracle.log (opt-in test, CUHE_B200_SLOW=1, ~11 min of CPU).  That run goes
+through every domain of the path (CRT, NTT, Barrett, ICRT, relin, modswitch), so the oracle is
+PINNED end to end by a reference known answer; a wrong intermediate table (CRT primes, ICRT
+constants, modswitch rounding, Barrett polynomials) destroys the decryption.  What no reference
+test pins is the exact VALUE of intermediate ciphertext words (the reference stores none and seeds
+keys with time(NULL)); those rest on the literal restatement here plus exact ring arithmetic
+(tests/golden/make_golden.py).
 """
 from __future__ import annotations
 
