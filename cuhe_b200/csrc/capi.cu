@@ -978,9 +978,24 @@ int cuhe_mul_raw_host_batch(cuhe_ctx* c, uint32_t* out_h, const uint32_t* a_h, c
         // three-stage pipeline over chunks of the batch: H2D | compute | D2H on separate streams, so
         // PCIe transfers in both directions overlap the kernels (the reference's z2r/r2z are
         // synchronous per polynomial, cuhe/CuHE.cu:317-348)
-        // chunks of 8 products keep every launch large enough to fill the GPU; smaller batches run as one chunk
-        const int chunk = batch >= 16 ? 8 : batch;
-        const int nchunk = (batch + chunk - 1) / chunk;
+        // chunk schedule: large chunks run the kernels at their best rate, but the first chunk's upload and
+        // the last chunk's download are exposed, so big batches ramp  C/2, C, C, ..., C/2.  Small batches
+        // run as one chunk.  CUHE_B200_HOST_CHUNK / CUHE_B200_HOST_RAMP override (tuning only).
+        static const int env_chunk = [] { const char* e = getenv("CUHE_B200_HOST_CHUNK"); return e ? atoi(e) : 0; }();
+        static const int env_ramp = [] { const char* e = getenv("CUHE_B200_HOST_RAMP"); return e ? atoi(e) : -1; }();
+        int base = env_chunk > 0 ? env_chunk : (batch >= 64 ? 16 : 8);
+        if (batch < 16) base = batch;
+        const bool ramp = env_ramp >= 0 ? env_ramp != 0 : (batch >= 4 * base && base >= 8);
+        std::vector<int> sizes;
+        {
+            int left = batch;
+            if (ramp) { sizes.push_back(base / 2); left -= base / 2; }
+            const int tail = ramp ? base / 2 : 0;
+            while (left - tail >= base) { sizes.push_back(base); left -= base; }
+            if (left - tail > 0) { sizes.push_back(left - tail); left = tail; }
+            if (tail) sizes.push_back(tail);
+        }
+        const int nchunk = (int)sizes.size();
         cudaEvent_t ready;
         CK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
         CK(cudaEventRecord(ready, st));                      // order after the caller's stream
@@ -993,8 +1008,8 @@ int cuhe_mul_raw_host_batch(cuhe_ctx* c, uint32_t* out_h, const uint32_t* a_h, c
         CK(cudaMemsetAsync(ro.p, 0, (size_t)batch * poly_w * 4, c->s_comp));
         std::vector<cudaEvent_t> ev(2 * nchunk);
         for (auto& e : ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        for (int i = 0; i < nchunk; i++) {
-            const int b0 = i * chunk, nb = std::min(chunk, batch - b0);
+        for (int i = 0, b0 = 0; i < nchunk; b0 += sizes[i], i++) {
+            const int nb = sizes[i];
             const size_t off = (size_t)b0 * poly_w, bytes = (size_t)nb * poly_w * 4;
             CK(cudaMemcpyAsync(ra.as<uint32_t>() + off, a_h + off, bytes, cudaMemcpyHostToDevice, c->s_h2d));
             CK(cudaMemcpyAsync(rb.as<uint32_t>() + off, b_h + off, bytes, cudaMemcpyHostToDevice, c->s_h2d));

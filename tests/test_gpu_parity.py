@@ -519,3 +519,30 @@ def test_large_prime_counts_mul(lib, ps):
         assert np.array_equal(out, o.icrt(o.mul_raw_to_crt(ra, rb, 0), 0))
     finally:
         e.close()
+
+
+@pytest.mark.parametrize("batch", [1, 5, 16, 37, 70])
+def test_mul_raw_host_batch_pipeline(eng16, batch):
+    """cuhe_mul_raw_host_batch: the three-stream H2D | kernels | D2H pipeline with its ramped chunk
+    schedule (one chunk below 16 products, 4-8-...-4 from 32, 8-16-...-8 from 64) returns, for every
+    product of the batch, exactly what the oracle computes."""
+    e, o = eng16, eng16.orc
+    W, H, n = o.W(0), o.H, o.n
+    rng = np.random.default_rng(100 + batch)
+    top_bits = o.moduli[0].bit_length() - 1 - 32 * (W - 1)            # keep every coefficient below q0
+    def polys():
+        x = rng.integers(0, 1 << 32, size=(batch, H, W), dtype=np.uint32)
+        x[:, :, W - 1] &= np.uint32((1 << top_bits) - 1)
+        x[:, n:, :] = 0
+        return x
+    a, b = polys(), polys()
+    torch = e.torch
+    ah = torch.from_numpy(a.view(np.int32)).pin_memory()
+    bh = torch.from_numpy(b.view(np.int32)).pin_memory()
+    oh = torch.full((batch, H, W), -1, dtype=torch.int32).pin_memory()
+    e.call("cuhe_mul_raw_host_batch", C.c_void_p(oh.data_ptr()), C.c_void_p(ah.data_ptr()), C.c_void_p(bh.data_ptr()),
+           0, batch, e.st())
+    torch.cuda.synchronize()
+    got = oh.numpy().view(np.uint32)
+    want = o.mul_raw_batch(a, b, 0)
+    assert np.array_equal(got, want)
