@@ -112,6 +112,9 @@ CPU_BATCH = 8      # products in flight per CPU step: 8 x 24 (polynomial, residu
 
 def _cpu_setup():
     from oracle.oracle import Oracle, lib
+    # every host thread this process may run on, whatever OMP_NUM_THREADS says (torchrun exports 1 to its
+    # workers, which would make the N>1 reference arm single-threaded)
+    lib().orc_set_threads(C.c_int(int(os.environ.get("CUHE_B200_CPU_THREADS", len(os.sched_getaffinity(0))))))
     o = Oracle(*WORKLOAD)
     o.barrett_tables()
     rng = random.Random(1)

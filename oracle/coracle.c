@@ -406,6 +406,16 @@ void orc_mul_raw_batch(uint32_t *dst_raw, const uint32_t *a_raw, const uint32_t 
     free(ca); free(cb); free(hold); free(cr);
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm of bench.py sets the count explicitly */
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+    extern void omp_set_num_threads(int);
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_max_threads(void) {
 #ifdef _OPENMP
     extern int omp_get_max_threads(void);
