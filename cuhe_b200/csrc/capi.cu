@@ -313,6 +313,12 @@ __global__ void modp_batch_kernel(int op, uint64_t* __restrict__ out, const uint
     if (op == 0) r = add_modP(a, y[i]);
     else if (op == 1) r = sub_modP(a, y[i]);
     else if (op == 2) r = mul_modP(a, y[i]);
+    else if (op == 4) {                      // the key-switch accumulator: sum of `shift` unreduced products, folded once
+        MacAcc acc{0, 0, 0, 0, 0, 0, 0, 0};
+        for (int k = 0; k < shift; k++) { const size_t j = (i + (size_t)k) % n; mac_wide(acc, x[j], y[j]); }
+        r = mac_fold(acc);
+    }
+    else if (op == 5) r = canon(a);
     else r = shl_dispatch<0>(a, shift);
     out[i] = r;
 }
@@ -882,8 +888,23 @@ int cuhe_relin(cuhe_ctx* c, uint64_t* dst, const uint32_t* raw, int lvl, cuhe_st
         Pass2Args b{};
         b.dst = D.as<uint64_t>(); b.tw2 = pl.tw2; b.dst_stride = N; b.row_mod = 1;
         run_ntt(c, pl, IN_DIGIT, OUT_U64, a, b, K, st);
-        dim3 grid((N + 255) / 256, rows);
-        relin_mac_kernel<<<grid, 256, 0, st>>>(dst, D.as<uint64_t>(), c->d_ek, K, (long long)N, (long long)K0 * N, 0, 1, N);
+        // CUHE_B200_RELIN_RB = 1 (generation 1 kernel), 2 or 4 rows per thread, CUHE_B200_RELIN_UNROLL = 1, 2, 4:
+        // A/B switches, tuning only.  Default: 2 rows, unroll 2 (fastest measured at 44 primes / 66 keys).
+        static const int mac_rb = [] { const char* e = getenv("CUHE_B200_RELIN_RB"); return e ? atoi(e) : 2; }();
+        static const int mac_un = [] { const char* e = getenv("CUHE_B200_RELIN_UNROLL"); return e ? atoi(e) : 2; }();
+        const long long ks = N, ps = (long long)K0 * N;
+        uint64_t* Dp = D.as<uint64_t>();
+        if (mac_rb == 1) {
+            dim3 grid((N + 255) / 256, rows);
+            relin_mac_kernel<<<grid, 256, 0, st>>>(dst, Dp, c->d_ek, K, ks, ps, 0, 1, N);
+        } else {
+            const int rb = mac_rb == 4 ? 4 : 2;
+            dim3 grid(N / 2 / 128, (rows + rb - 1) / rb);
+#define CUHE_MAC(RB_, UN_) relin_mac_kernel_v2<RB_, UN_><<<grid, 128, 0, st>>>(dst, Dp, c->d_ek, K, ks, ps, 0, 1, N, rows)
+            if (rb == 4) { if (mac_un == 1) CUHE_MAC(4, 1); else if (mac_un == 4) CUHE_MAC(4, 4); else CUHE_MAC(4, 2); }
+            else { if (mac_un == 1) CUHE_MAC(2, 1); else if (mac_un == 4) CUHE_MAC(2, 4); else CUHE_MAC(2, 2); }
+#undef CUHE_MAC
+        }
         count_launch();
         CK(cudaGetLastError());
     });
@@ -914,8 +935,9 @@ int cuhe_intt_batch(cuhe_ctx* c, uint64_t* dst, const uint64_t* src, int nttLen,
 int cuhe_modp_batch(cuhe_ctx* c, int op, uint64_t* out, const uint64_t* x, const uint64_t* y, size_t n, int shift,
                     cuhe_stream stream) {
     return guarded([&] {
-        REQUIRE(c && out && x, "null argument"); REQUIRE(op >= 0 && op <= 3, "bad op");
-        REQUIRE(op == 3 || y, "null argument"); REQUIRE(shift >= 0 && shift < 192, "shift out of range");
+        REQUIRE(c && out && x, "null argument"); REQUIRE(op >= 0 && op <= 5, "bad op");
+        REQUIRE(op == 3 || op == 5 || y, "null argument");
+        REQUIRE(shift >= 0 && (op == 4 ? shift <= 65536 : shift < 192), "shift out of range");
         DeviceGuard dg(c->device);
         if (n == 0) return;
         modp_batch_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(op, out, x, y, n, shift);

@@ -24,13 +24,9 @@ namespace cuhe_b200 {
 constexpr uint64_t kP = 0xFFFFFFFF00000001ULL;
 constexpr uint64_t kEps = 0xFFFFFFFFULL;  // 2^64 mod P
 
-// any 64-bit representative -> [0,P)
-__device__ __forceinline__ uint64_t canon(uint64_t x) {
-    uint32_t m;
-    asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, 0xffffffff;\n\taddc.cc.u32 t, %2, 0;\n\tsubc.u32 %0, 0, 0;\n\t}"
-        : "=r"(m) : "r"((uint32_t)x), "r"((uint32_t)(x >> 32)));
-    return x + (uint64_t)m;
-}
+// (carry-flag convention: after add.cc CF is the carry, after sub.cc CF is the NOT-borrow that subc
+// consumes -- so masks are always derived with addc after an add chain and subc after a sub chain,
+// never mixed)
 // d - m (mod 2^64) for a mask m in {0, 2^32-1}.  (Measured alternative: d + m*(2^32-1) - (m<<32)
 // moves this correction to the FMA pipe -- ALU-pipe instructions of a 64-point transform drop
 // 3275 -> 2335 -- but the batched 64K transform got 8 % slower on B200, so the plain form stays.)
@@ -48,6 +44,8 @@ __device__ __forceinline__ uint64_t add_reduce(uint64_t a, uint64_t me) {
     asm("{\n\tadd.cc.u64 %0, %2, %3;\n\taddc.u32 %1, 0xffffffff, 0;\n\t}" : "=l"(z), "=r"(k) : "l"(a), "l"(me));
     return sub_mask(z, k);            // k = 0 on carry, 0xffffffff otherwise
 }
+// any 64-bit representative -> [0,P): x + 0 < 2P, so one conditional -P
+__device__ __forceinline__ uint64_t canon(uint64_t x) { return add_reduce(x, kEps); }
 // (a - b) mod P                                              (ModP.h:240-247)
 __device__ __forceinline__ uint64_t sub_modP(uint64_t a, uint64_t b) { return sub_fix(a, b); }
 // (a + b) mod P = a - (P - b); P - b is in [1, P]            (ModP.h:230-239)

@@ -197,7 +197,10 @@ int cuhe_icrt_slice_batch(cuhe_ctx* ctx, uint32_t* raw_slice_out, const uint32_t
 
 /* ---- device mod-P primitives on arrays: what tests/test_ModP.cu:57-137 drives
  *      (_add/_sub/_mul/_ls_modP of cuhe/ModP.h:68-289).  op: 0 add, 1 sub, 2 mul,
- *      3 shift-left by `shift` bits (0 <= shift < 192).  out[i] = x[i] op y[i].
+ *      3 shift-left by `shift` bits (0 <= shift < 192), 4 the relinearization
+ *      accumulator: out[i] = sum_{k<shift} x[(i+k)%n]*y[(i+k)%n] mod P, products
+ *      summed unreduced and folded once; 5 canonical residue of ANY 64-bit x[i].
+ *      Otherwise out[i] = x[i] op y[i].
  *      Inputs must be canonical (< P), as in the reference's test. ------------- */
 int cuhe_modp_batch(cuhe_ctx* ctx, int op, uint64_t* out, const uint64_t* x, const uint64_t* y, size_t n, int shift,
                     cuhe_stream stream);

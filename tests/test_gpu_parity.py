@@ -546,3 +546,28 @@ def test_mul_raw_host_batch_pipeline(eng16, batch):
     got = oh.numpy().view(np.uint32)
     want = o.mul_raw_batch(a, b, 0)
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("terms", [1, 2, 66, 141, 1000])
+def test_modp_wide_accumulator(eng16, terms):
+    """The key-switch accumulator (160-bit unreduced sum of 64x64-bit products, folded once with
+    2^96 == -1, 2^128 == -2^32): equals big-integer arithmetic, including all-maximal operands."""
+    x, y = _modp_inputs(4096, 7 + terms)
+    n = x.size
+    x[200:264] = P - 1
+    y[200:264] = P - 1
+    out = eng16.empty(x.shape, np.uint64)
+    eng16.call("cuhe_modp_batch", 4, p(out), p(eng16.up(x)), p(eng16.up(y)), C.c_size_t(n), terms, eng16.st())
+    got = Eng.dn(out, np.uint64)
+    prod = (x.astype(object) * y.astype(object))
+    ext = np.concatenate([prod, prod[:terms]])
+    want = np.array([int(sum(ext[i:i + terms])) % P for i in range(n)], dtype=object)
+    assert np.array_equal(got.astype(object), want)
+
+
+def test_modp_canonical_residue(eng16):
+    x = np.array([0, 1, P - 1, P, P + 1, 2**64 - 1, 2**64 - 2**32, 2**63, 0xFFFFFFFF, 0xFFFFFFFF00000000], dtype=np.uint64)
+    x = np.concatenate([x, np.random.default_rng(3).integers(0, 2**64, size=4086, dtype=np.uint64)])
+    out = eng16.empty(x.shape, np.uint64)
+    eng16.call("cuhe_modp_batch", 5, p(out), p(eng16.up(x)), None, C.c_size_t(x.size), 0, eng16.st())
+    assert np.array_equal(Eng.dn(out, np.uint64).astype(object), x.astype(object) % P)
