@@ -184,6 +184,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         import datetime
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL prints its banner there)
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=90))   # fail fast on a mismatch
     lib = load_library()
     par = cuhe_params()
@@ -303,30 +305,81 @@ def run_ours(args):
     # ---- e2e: host buffers through the C ABI (the device part of mulZZX), H2D + D2H inside ----
     e2e = None
     if world > 1:
-        # every rank uploads the (replicated) operands from pinned host memory, the sharded
-        # multiply runs, rank 0 reads the complete RAW products back
-        ah = torch.from_numpy(a_np[0].view(np.int32)).pin_memory()
-        bh = torch.from_numpy(b_np[0].view(np.int32)).pin_memory()
-        oh = torch.zeros((B, H, W), dtype=torch.int32).pin_memory()
+        # data-parallel host side: rank r owns products [r*b, (r+1)*b) of every step.  Per step and rank:
+        # H2D of the owned operands from pinned memory -> NVLink all-gather of the RAW operands -> the
+        # residue-sharded multiply (all-to-all, sliced ICRT) -> all-to-all of RAW slices back to the
+        # owners -> D2H of the owned products.  Every polynomial crosses PCIe once per step in the whole
+        # job.  Copies run on side streams, double buffered, so step i+1's upload and step i-1's download
+        # overlap step i's kernels and collectives.
+        b = args.batch
+        lo = rank * b
+        ah = [torch.from_numpy(a_np[k][lo:lo + b].view(np.int32)).pin_memory() for k in range(2)]
+        bh = [torch.from_numpy(b_np[k][lo:lo + b].view(np.int32)).pin_memory() for k in range(2)]
+        oh = [torch.zeros((b, H, W), dtype=torch.int32).pin_memory() for _ in range(2)]
+        a_loc = [torch.zeros((b, H, W), dtype=torch.int32, device=dev) for _ in range(2)]
+        b_loc = [torch.zeros((b, H, W), dtype=torch.int32, device=dev) for _ in range(2)]
+        o_loc = [None, None]
+        s_in, s_comp, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        ev_in = [torch.cuda.Event() for _ in range(2)]          # operands of slot k are on the device
+        ev_used = [torch.cuda.Event() for _ in range(2)]        # slot k's operands have been gathered
+        ev_done = [torch.cuda.Event() for _ in range(2)]        # slot k's owned products are in o_loc[k]
+        ev_read = [torch.cuda.Event() for _ in range(2)]        # slot k's products have left the device
 
-        def e2e_step():
-            a_dev[0].copy_(ah, non_blocking=True)
-            b_dev[0].copy_(bh, non_blocking=True)
-            out = step(0)
-            if rank == 0:
-                oh.copy_(out, non_blocking=True)
-        for _ in range(2):
-            e2e_step()
+        def upload(i):
+            k = i % 2
+            with torch.cuda.stream(s_in):
+                if i >= 2:
+                    s_in.wait_event(ev_used[k])
+                a_loc[k].copy_(ah[k], non_blocking=True)
+                b_loc[k].copy_(bh[k], non_blocking=True)
+                ev_in[k].record(s_in)
+
+        def compute(i):
+            k = i % 2
+            with torch.cuda.stream(s_comp):
+                s_comp.wait_event(ev_in[k])
+                a_all = sh.all_gather_operands(a_loc[k], world)
+                b_all = sh.all_gather_operands(b_loc[k], world)
+                ev_used[k].record(s_comp)
+                check(lib.cuhe_mul_crt_batch(h, p(crt_loc), p(a_all), p(b_all), 0, B, st()))
+                crt_slice = sh.exchange_for_icrt(crt_loc, L, rank, world)
+                check(lib.cuhe_icrt_slice_batch(h, p(raw_slice), p(crt_slice), 0, cb, ce - cb, B, st()))
+                if i >= 2:
+                    s_comp.wait_event(ev_read[k])
+                o_loc[k] = sh.raw_slices_to_owners(raw_slice, world)
+                ev_done[k].record(s_comp)
+
+        def download(i):
+            k = i % 2
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_done[k])
+                oh[k].copy_(o_loc[k], non_blocking=True)
+                ev_read[k].record(s_out)
+
+        def e2e_run(nsteps):
+            upload(0)
+            for i in range(nsteps):
+                if i + 1 < nsteps:
+                    upload(i + 1)
+                compute(i)
+                download(i)
+            for s_ in (s_in, s_comp, s_out):
+                s_.synchronize()
+
+        torch.cuda.synchronize()
+        e2e_run(3)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
+        e2e_run(args.steps)
         barrier()
         el = time.perf_counter() - t0
         tt = torch.tensor([el], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": B * args.steps / float(tt.item()), "unit": "mul/s", "h2d_bytes_per_step": int(2 * B * H * W * 4) * world,
-               "d2h_bytes_per_step": int(B * H * W * 4), "api": "pinned host RAW (replicated to every rank) -> sharded cuhe_mul_crt_batch / all-to-all / cuhe_icrt_slice_batch / all-gather -> host on rank 0"}
+        e2e = {"value": B * args.steps / float(tt.item()), "unit": "mul/s", "h2d_bytes_per_step": int(2 * B * H * W * 4),
+               "d2h_bytes_per_step": int(B * H * W * 4),
+               "api": "each rank: pinned host RAW of its products -> H2D -> NVLink all-gather -> sharded cuhe_mul_crt_batch / "
+                      "all-to-all / cuhe_icrt_slice_batch / all-to-all to owners -> D2H (double-buffered side streams); "
+                      "byte counts are whole-job totals"}
     if world == 1:
         # one e2e step = one call with Be = 4*B products from pinned host memory; the library pipelines
         # H2D | kernels | D2H over chunks of 8 products inside the call

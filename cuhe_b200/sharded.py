@@ -78,6 +78,32 @@ def all_gather_raw_slices(mine: torch.Tensor, world: int, group=None) -> torch.T
     return gathered.view(world, B, Hs, W).permute(1, 0, 2, 3).reshape(B, world * Hs, W).contiguous()
 
 
+def all_gather_operands(mine: torch.Tensor, world: int, group=None) -> torch.Tensor:
+    """Data-parallel input: rank r uploaded products [r*b, (r+1)*b) -> every rank gets all world*b RAW
+    operands ([b][H][W] -> [world*b][H][W], product order) over NVLink, so each polynomial crosses
+    PCIe once in the whole job instead of once per rank."""
+    if world == 1:
+        return mine
+    out = torch.empty((world * mine.shape[0],) + tuple(mine.shape[1:]), dtype=mine.dtype, device=mine.device)
+    dist.all_gather_into_tensor(out, mine.contiguous(), group=group)
+    return out
+
+
+def raw_slices_to_owners(mine: torch.Tensor, world: int, group=None) -> torch.Tensor:
+    """mine: [world*b][H/G][W] = this rank's coefficient slice of every product -> [b][H][W], the
+    complete RAW result of the products this rank owns (products r*b.. on rank r).  An all-to-all:
+    1/world of the traffic of all_gather_raw_slices when every rank only reads its own products back."""
+    if world == 1:
+        return mine
+    B, Hs, W = mine.shape
+    assert B % world == 0
+    b = B // world
+    send = mine.contiguous()                                       # [owner][b][Hs][W]
+    recv = torch.empty_like(send)                                  # [source rank = slice][b][Hs][W]
+    dist.all_to_all_single(recv.view(world * b, Hs, W), send.view(world * b, Hs, W), group=group)
+    return recv.view(world, b, Hs, W).permute(1, 0, 2, 3).reshape(b, world * Hs, W).contiguous()
+
+
 def coefficient_slice(H: int, rank: int, world: int) -> Tuple[int, int]:
     step = (H + world - 1) // world
     return min(rank * step, H), min((rank + 1) * step, H)

@@ -64,6 +64,16 @@ def _worker(rank, world, port, q):
             raw_sl[i] = o.icrt(got[i], lvl)[rank * Hs:(rank + 1) * Hs]
         raw_all2 = sh.all_gather_raw_slices(torch.from_numpy(raw_sl.view(np.int32)), world).numpy().view(np.uint32)
         assert np.array_equal(raw_all2, raws)
+        # data-parallel front and back: rank r uploads products [r*b, (r+1)*b), everybody gets all of
+        # them; after the sliced ICRT every rank gets back the complete results of ITS products only
+        Bw = 2 * world
+        allp = np.arange(Bw * H * W, dtype=np.uint32).reshape(Bw, H, W) * np.uint32(2654435761)
+        own = allp[rank * 2:(rank + 1) * 2]
+        gathered = sh.all_gather_operands(torch.from_numpy(own.view(np.int32).copy()), world).numpy().view(np.uint32)
+        assert np.array_equal(gathered, allp)
+        my_slice = np.ascontiguousarray(allp[:, rank * Hs:(rank + 1) * Hs])          # slice `rank` of every product
+        back = sh.raw_slices_to_owners(torch.from_numpy(my_slice.view(np.int32).copy()), world).numpy().view(np.uint32)
+        assert np.array_equal(back, own), "slice-to-owner exchange does not rebuild the owned products"
         # modswitch: owner of the last prime broadcasts its row
         owner, row = sh.owner_of(L - 1, world)
         assert owner == (L - 1) % world and sh.local_primes(L, owner, world)[row] == L - 1
