@@ -43,6 +43,23 @@ def peaks():
         return {"hbm_gbs": 6650.0}, "fallback"
 
 
+def ntt_issue(batch, launch_ms):
+    """Secondary roofline of the NTT kernels, which are integer-ALU bound: warp instructions per launch
+    pair (smsp__inst_executed.sum of the committed ncu capture) / measured launch time, against the issue
+    peak 148 SMs x 4 schedulers x SM clock; plus the ALU-pipe utilisation ncu reported for the capture."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ntt_traffic.json")))
+        if t["batch"] != batch:
+            return None
+        rate = t["warp_instructions_per_launch_pair"] / (launch_ms * 1e-3)
+        peak = 148 * 4 * 1.965e9
+        return {"bound": "int32 alu pipe (16 lanes per scheduler: IADD3/LOP3/SHF issue every other cycle)",
+                "warp_inst_per_s": rate, "issue_peak_warp_inst_per_s": peak, "issue_frac": rate / peak,
+                "alu_pipe_pct_of_peak_ncu": t["alu_pipe_pct_of_peak"], "source": "profiles/r01_v2b_ntt_full.txt"}
+    except Exception:
+        return None
+
+
 def ntt_traffic(batch):
     """dram__bytes_read+write of the two NTT pass kernels for one launch pair at this batch, from the
     committed ncu --set full capture (profiles/ntt_traffic.json); None if it was taken at another batch."""
@@ -299,6 +316,7 @@ def run_ours(args):
                 "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
                 "peak_source": pk_src + " (burst copy bandwidth)", "traffic": ntt_traffic(cnt),
                 "algorithmic_bytes_per_launch": NTT_BYTES_64K * cnt, "launch_ms": kms, "batch": cnt,
+                "secondary": ntt_issue(cnt, kms),
                 "note": "INT32-ALU bound (SURVEY F9): see DESIGN.md for the instruction-issue roofline"}
         del src, dst
 
