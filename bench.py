@@ -127,11 +127,26 @@ def gen_raw(o, batch, nbuf, seed):
 CPU_BATCH = 8      # products in flight per CPU step: 8 x 24 (polynomial, residue) tasks keep every host thread busy
 
 
+def _host_threads() -> int:
+    """One thread per physical core this process may run on (measured on the 64-core / 128-thread B200
+    host: 12.3 mul/s with 64 threads, 3.4 with 128).  Set explicitly because torchrun exports
+    OMP_NUM_THREADS=1 to its workers, which would make the N>1 reference arm single-threaded."""
+    if os.environ.get("CUHE_B200_CPU_THREADS"):
+        return int(os.environ["CUHE_B200_CPU_THREADS"])
+    cpus = sorted(os.sched_getaffinity(0))
+    cores = set()
+    try:
+        for c in cpus:
+            base = f"/sys/devices/system/cpu/cpu{c}/topology/"
+            cores.add((open(base + "physical_package_id").read().strip(), open(base + "core_id").read().strip()))
+        return max(1, len(cores))
+    except OSError:
+        return max(1, len(cpus))
+
+
 def _cpu_setup():
     from oracle.oracle import Oracle, lib
-    # every host thread this process may run on, whatever OMP_NUM_THREADS says (torchrun exports 1 to its
-    # workers, which would make the N>1 reference arm single-threaded)
-    lib().orc_set_threads(C.c_int(int(os.environ.get("CUHE_B200_CPU_THREADS", len(os.sched_getaffinity(0))))))
+    lib().orc_set_threads(C.c_int(_host_threads()))
     o = Oracle(*WORKLOAD)
     o.barrett_tables()
     rng = random.Random(1)

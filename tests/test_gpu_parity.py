@@ -34,12 +34,14 @@ class Eng:
         self.h = C.c_void_p()
         check(lib.cuhe_ctx_create(C.byref(self.h), C.byref(self.par), device, rank, world))
         self.orc = get_oracle(ps)
+        self._keep = []
         self.dev = f"cuda:{device}"
         if with_polymod:
             phi = np.array(self.orc.phi, dtype=np.int64)
             check(lib.cuhe_ctx_set_poly_modulus_host(self.h, phi.ctypes.data_as(C.c_void_p), len(phi)))
 
     def close(self):
+        self._keep.clear()
         self.lib.cuhe_ctx_destroy(self.h)
 
     def st(self):
@@ -48,7 +50,12 @@ class Eng:
     def up(self, a: np.ndarray):
         a = np.ascontiguousarray(a)
         view = a.view(np.int32) if a.dtype == np.uint32 else a.view(np.int64)
-        return self.torch.from_numpy(view).to(self.dev)
+        t = self.torch.from_numpy(view).to(self.dev)
+        self._keep.append(t)          # p(e.up(x)) passes only the address: keep the tensor alive until close()
+        if len(self._keep) > 64:
+            self.torch.cuda.synchronize()
+            del self._keep[:32]
+        return t
 
     def empty(self, shape, dt):
         t = self.torch
@@ -557,7 +564,8 @@ def test_modp_wide_accumulator(eng16, terms):
     x[200:264] = P - 1
     y[200:264] = P - 1
     out = eng16.empty(x.shape, np.uint64)
-    eng16.call("cuhe_modp_batch", 4, p(out), p(eng16.up(x)), p(eng16.up(y)), C.c_size_t(n), terms, eng16.st())
+    dx, dy = eng16.up(x), eng16.up(y)                       # keep both alive: p() only takes the address
+    eng16.call("cuhe_modp_batch", 4, p(out), p(dx), p(dy), C.c_size_t(n), terms, eng16.st())
     got = Eng.dn(out, np.uint64)
     prod = (x.astype(object) * y.astype(object))
     ext = np.concatenate([prod, prod[:terms]])
@@ -569,5 +577,6 @@ def test_modp_canonical_residue(eng16):
     x = np.array([0, 1, P - 1, P, P + 1, 2**64 - 1, 2**64 - 2**32, 2**63, 0xFFFFFFFF, 0xFFFFFFFF00000000], dtype=np.uint64)
     x = np.concatenate([x, np.random.default_rng(3).integers(0, 2**64, size=4086, dtype=np.uint64)])
     out = eng16.empty(x.shape, np.uint64)
-    eng16.call("cuhe_modp_batch", 5, p(out), p(eng16.up(x)), None, C.c_size_t(x.size), 0, eng16.st())
+    dx = eng16.up(x)
+    eng16.call("cuhe_modp_batch", 5, p(out), p(dx), None, C.c_size_t(x.size), 0, eng16.st())
     assert np.array_equal(Eng.dn(out, np.uint64).astype(object), x.astype(object) % P)
