@@ -463,6 +463,20 @@ class CuCtxt(CuPolynomial):
         self.logq_ -= param.logCoeffCut
         self.level_ += 1
 
+    def dropToLevel(self, lvl, st=None):
+        """EXTENSION (not in the reference): the same ciphertext modulo q_lvl, on the device.  q_lvl is the
+        product of the first numCrtPrime(lvl) primes, so in the CRT domain `c mod q_lvl` is just the first
+        rows -- the device-resident form of the host-side `coeffReduce(x, x, lvl); setLevel(lvl, ...)` that
+        examples/Prince/Prince.cu:192-193,210-213 performs on ZZX values between S-box layers."""
+        if lvl < self.level_:
+            raise CuHEError("Error: dropToLevel cannot raise the modulus!")
+        if lvl == self.level_:
+            return
+        self.x2c(st)
+        self.cRep_ = self.cRep_[:param._numCrtPrime(lvl)].clone()
+        self.level_ = lvl
+        self.logq_ = param._logCoeff(lvl)
+
     def relin(self, st=None):
         """cuhe/CuHE.cu:570-581"""
         if not _evalkeys_loaded:

@@ -97,6 +97,15 @@ class OracleEngine:
                 self.c, self.domain_, self.isProd_ = None, 3, True
                 self.x2c()
 
+            def dropToLevel(self, lvl):
+                if lvl < self.level_:
+                    raise OracleEngine.Error("Error: dropToLevel cannot raise the modulus!")
+                if lvl == self.level_:
+                    return
+                self.x2c()
+                self.c = np.ascontiguousarray(self.c[:eng.param._numCrtPrime(lvl)])
+                self.level_ = lvl
+
             def modSwitch(self):
                 par = eng.param
                 if self.logq() < par.logCoeffMin + par.logCoeffCut:

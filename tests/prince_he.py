@@ -237,10 +237,7 @@ class HomOps:
     def _sbox(self, bits, lvl, anf):
         ch = self.ch
         C = ch.CuCtxt
-        x = [C() for _ in range(4)]
-        for c, v in zip(x, bits):
-            c.setLevel(lvl, 0, v)
-            c.x2n()
+        x = self._inputs(bits, lvl)
         pairs = {}
         for i in range(4):
             for j in range(i + 1, 4):
@@ -286,26 +283,117 @@ class HomOps:
                 if len(mono) == 3:
                     ch.cXor(acc, acc, triples[mono])
             assert not any(len(mono) == 4 for mono in monos)
-        res = []
         for acc in outs:
             acc.relin()
             acc.modSwitch()
             self.counts["relin"] += 1
             self.counts["modSwitch"] += 1
-            acc.x2z()
-            res.append(acc.zRep())
-            acc.reset()
         for c in x + list(pairs.values()) + list(triples.values()):
             c.reset()
         self.counts["sbox"] += 1
+        return self._outputs(outs)
+
+    def _inputs(self, bits, lvl):
+        """ZZX values from the host, as the reference does (Prince.cu:210-217)"""
+        x = [self.ch.CuCtxt() for _ in range(4)]
+        for c, v in zip(x, bits):
+            c.setLevel(lvl, 0, v)
+            c.x2n()
+        return x
+
+    def _outputs(self, outs):
+        """back to host ZZX values (Prince.cu:315-320)"""
+        res = []
+        for acc in outs:
+            acc.x2z()
+            res.append(acc.zRep())
+            acc.reset()
         return res
 
+    def upload(self, zzx):
+        return zzx
 
-def hom_prince(ch, dhs, msg_bits, k0_bits, k1_bits, check_rounds=(), log=None):
+    def to_zzx(self, c):
+        return c
+
+
+class DeviceHomOps(HomOps):
+    """the same evaluation with every ciphertext bit RESIDENT ON THE DEVICE, in the CRT
+    domain, for the whole cipher.  Linear layers are cXor / cNot on the device instead of host ZZX
+    additions, fresh key bits are brought to the current level with CuCtxt.dropToLevel (an extension:
+    keep the first rows) instead of a host coeffReduce + re-upload, and an S-box layer consumes and
+    produces device ciphertexts: no polynomial crosses PCIe between encryption and decryption (the
+    reference moves 768 polynomials each way, Prince.cu:204-322)."""
+
+    def __init__(self, ch, dhs):
+        super().__init__(ch, dhs)
+        self._views = {}
+
+    def upload(self, zzx):
+        c = self.ch.CuCtxt()
+        c.setLevel(0, 0, zzx)
+        c.x2c()
+        return c
+
+    def _at_level(self, c, lvl):
+        if c.level() == lvl:
+            return c
+        key = (id(c), lvl)
+        if key not in self._views:                      # only the long-lived key bits ever need this
+            v = self.ch.CuCtxt()
+            self.ch.copy(v, c)
+            v.dropToLevel(lvl)
+            self._views[key] = (v, c)                   # keep `c` alive so that id(c) stays unique
+        return self._views[key][0]
+
+    def add(self, x, y):
+        lvl = max(x.level(), y.level())
+        out = self.ch.CuCtxt()
+        self.ch.cXor(out, self._at_level(x, lvl), self._at_level(y, lvl))
+        return out
+
+    def add_const(self, x, bit):
+        if not bit:
+            return x
+        out = self.ch.CuCtxt()
+        self.ch.cNot(out, x)                            # + (p - 1) = + 1 on coefficient 0 for p = 2
+        return out
+
+    def finish(self, state):
+        return state
+
+    def sbox_layer(self, state, inverse):
+        out = []
+        for i in range(16):
+            out += self._sbox(state[4 * i:4 * i + 4], self.level, ANF_INV if inverse else ANF_FWD)
+        self.level += 2
+        self._views = {k: v for k, v in self._views.items() if k[1] >= self.level}
+        return out
+
+    def _inputs(self, bits, lvl):
+        x = []
+        for c in bits:
+            t = self.ch.CuCtxt()
+            self.ch.copy(t, self._at_level(c, lvl))     # the S-box transforms its inputs in place
+            t.x2n()
+            x.append(t)
+        return x
+
+    def _outputs(self, outs):
+        return outs                                      # CRT domain, two levels down, still on the device
+
+    def to_zzx(self, c):
+        t = self.ch.CuCtxt()
+        self.ch.copy(t, c)
+        t.x2z()
+        return t.zRep()
+
+
+def hom_prince(ch, dhs, msg_bits, k0_bits, k1_bits, check_rounds=(), log=None, resident=False):
     """Encrypt the 192 input bits at level 0 (Prince.cu:68-81), evaluate, decrypt at the last level
     (Prince.cu:91-94).  Returns (decrypted 64 bits, HomOps)."""
-    ops = HomOps(ch, dhs)
-    enc = lambda b: dhs.encrypt([b], 0)
+    ops = DeviceHomOps(ch, dhs) if resident else HomOps(ch, dhs)
+    enc = lambda b: ops.upload(dhs.encrypt([b], 0))
     msg = [enc(b) for b in msg_bits]
     k0 = [enc(b) for b in k0_bits]
     k1 = [enc(b) for b in k1_bits]
@@ -316,13 +404,13 @@ def hom_prince(ch, dhs, msg_bits, k0_bits, k1_bits, check_rounds=(), log=None):
         if log:
             log(f"round {r}: S-box layer done, level {ops.level}")
         if r in check_rounds:
-            bits = [dhs.decrypt(x, ops.level)[0] for x in s]
+            bits = [dhs.decrypt(ops.to_zzx(x), ops.level)[0] for x in s]
             got_rounds[r] = bits
             if log:
                 log(f"round {r}: {''.join(map(str, bits))}")
 
     out = prince_eval(ops, msg, k0, k1, on_round=on_round)
     last = dhs.par.depth - 1
-    bits = [dhs.decrypt(x, last)[0] for x in out]
+    bits = [dhs.decrypt(ops.to_zzx(x), last)[0] for x in out]
     ops.round_bits, ops.round_want = got_rounds, {r: want[r] for r in got_rounds}
     return bits, ops

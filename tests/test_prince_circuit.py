@@ -104,19 +104,47 @@ def test_homomorphic_sbox_on_the_oracle_engine():
     assert ops.counts == dict(cAnd=20, relin=12, modSwitch=28, sbox=2)   # 10 / 6 / 14 per S-box
 
 
+def test_device_resident_sbox_and_key_addition_on_the_oracle_engine():
+    """The device-resident form: ciphertexts stay CuCtxt objects in the CRT domain, fresh
+    key bits are brought to the current level with dropToLevel, linear steps are cXor / cNot."""
+    ps = (5, 2, 16, 25, 25, 8191)
+    eng, dhs = _engine_and_keys(ps, seed=4)
+    ops = ph.DeviceHomOps(eng, dhs)
+    rng = random.Random(10)
+    bits = [rng.randrange(2) for _ in range(4)]
+    key = [rng.randrange(2) for _ in range(4)]
+    cts = [ops.upload(dhs.encrypt([b], 0)) for b in bits]
+    kts = [ops.upload(dhs.encrypt([b], 0)) for b in key]           # level 0, used again two levels down
+    out = ops._sbox(cts, 0, ph.ANF_FWD)
+    assert all(c.level() == 2 and c.domain() == 2 for c in out)
+    v = ph.SBOX[int("".join(map(str, bits)), 2)]
+    sb = [(v >> 3) & 1, (v >> 2) & 1, (v >> 1) & 1, v & 1]
+    assert [dhs.decrypt(ops.to_zzx(c), 2)[0] for c in out] == sb
+    ops.level = 2
+    mixed = [ops.add_const(ops.add(c, k), 1) for c, k in zip(out, kts)]       # state + key + 1 at level 2
+    assert all(k.level() == 0 for k in kts)                                    # the keys themselves are untouched
+    want = [s ^ k ^ 1 for s, k in zip(sb, key)]
+    assert [dhs.decrypt(ops.to_zzx(c), 2)[0] for c in mixed] == want
+    back = ops._sbox(mixed, 2, ph.ANF_INV)
+    w = ph.SBOX_INV[int("".join(map(str, want)), 2)]
+    assert [dhs.decrypt(ops.to_zzx(c), 4)[0] for c in back] == [(w >> 3) & 1, (w >> 2) & 1, (w >> 1) & 1, w & 1]
+
+
 @pytest.mark.skipif(os.environ.get("CUHE_B200_SLOW") != "1", reason="~20 min of CPU; set CUHE_B200_SLOW=1")
-def test_full_prince_on_the_oracle_engine():
+@pytest.mark.parametrize("resident", [False, True], ids=["host_linear_layers", "device_resident"])
+def test_full_prince_on_the_oracle_engine(resident):
     import time
     eng, dhs = _engine_and_keys(ph.PRINCE_PARAMS, seed=2026)
     t0 = time.time()
-    log_path = os.path.join(os.path.dirname(__file__), "golden", "prince_kat_oracle.log")
+    log_path = os.path.join(os.path.dirname(__file__), "golden",
+                            "prince_kat_oracle_resident.log" if resident else "prince_kat_oracle.log")
     lines = []
 
     def log(msg):
         lines.append(f"[{time.time() - t0:7.1f} s] {msg}")
         print(lines[-1], flush=True)
 
-    bits, ops = ph.hom_prince(eng, dhs, [0] * 64, [1] * 64, [0] * 64, check_rounds=(0, 5, 11), log=log)
+    bits, ops = ph.hom_prince(eng, dhs, [0] * 64, [1] * 64, [0] * 64, check_rounds=(0, 5, 11), log=log, resident=resident)
     log("decrypted: " + "".join(map(str, bits)))
     log("expected : " + REFERENCE_FINAL)
     log(f"op counts: {ops.counts}")
