@@ -47,22 +47,30 @@ def test_sbox_ciphertexts_equal_oracle_engine():
         ch.resetParameters()
 
 
-def test_homomorphic_prince_known_answer():
+@pytest.fixture(scope="module")
+def prince_keys():
     from dhs_host import DHS
     ch = _gpu()
     o = get_oracle(ph.PRINCE_PARAMS)
     t0 = time.time()
-    try:
-        dhs = DHS(ch, *ph.PRINCE_PARAMS, phi=o.phi, seed=2026)
-        t_keys = time.time() - t0
-        ch.launch_count(reset=True)
-        t1 = time.time()
-        bits, ops = ph.hom_prince(ch, dhs, [0] * 64, [1] * 64, [0] * 64, check_rounds=(0, 11))
-        t_eval = time.time() - t1
-        print(f"\nkeygen {t_keys:.1f} s, encrypt+evaluate+decrypt {t_eval:.1f} s, ops {ops.counts}, "
-              f"kernel launches {ch.launch_count()}")
-        assert ops.counts == dict(cAnd=1920, relin=1152, modSwitch=2688, sbox=192)
-        assert ops.round_bits == ops.round_want
-        assert ph.bits_to_hex(bits) == ph.KAT_HEX
-    finally:
-        ch.resetParameters()
+    dhs = DHS(ch, *ph.PRINCE_PARAMS, phi=o.phi, seed=2026)
+    print(f"\nkeygen {time.time() - t0:.1f} s")
+    yield ch, dhs
+    ch.resetParameters()
+
+
+@pytest.mark.parametrize("resident", [False, True], ids=["host_linear_layers", "device_resident"])
+def test_homomorphic_prince_known_answer(prince_keys, resident):
+    """host_linear_layers: the reference's flow (ZZX values on the host between S-box layers,
+    Prince.cu:146-189, 460-468).  device_resident: SURVEY 8(f) N2 -- every ciphertext stays on the device
+    from encryption to decryption (cXor / cNot / dropToLevel for the linear layers)."""
+    ch, dhs = prince_keys
+    ch.launch_count(reset=True)
+    t1 = time.time()
+    bits, ops = ph.hom_prince(ch, dhs, [0] * 64, [1] * 64, [0] * 64, check_rounds=(0, 11), resident=resident)
+    t_eval = time.time() - t1
+    print(f"\n{'device-resident' if resident else 'host linear layers'}: encrypt+evaluate+decrypt {t_eval:.1f} s, "
+          f"ops {ops.counts}, kernel launches {ch.launch_count()}")
+    assert ops.counts == dict(cAnd=1920, relin=1152, modSwitch=2688, sbox=192)
+    assert ops.round_bits == ops.round_want
+    assert ph.bits_to_hex(bits) == ph.KAT_HEX
