@@ -236,7 +236,8 @@ def run_ours(args):
     info = dict(q0=int.from_bytes(qw.tobytes(), "little"), W=W, H=H, n=n)
     # per-GPU work is held constant: every step multiplies batch*world ciphertext pairs, the residue
     # axis of all of them sharded over the ranks (weak scaling; the all-gather grows with the batch)
-    B, NBUF = args.batch * world, 4
+    B = args.batch * world
+    NBUF = 4 if B <= 64 else 2      # rotating operand sets (each is B x 4.7 MB on the host and on the device)
     a_np, b_np = gen_raw(info, B, NBUF, 20260924)
     a_dev = torch.from_numpy(a_np.view(np.int32)).to(dev)
     b_dev = torch.from_numpy(b_np.view(np.int32)).to(dev)
