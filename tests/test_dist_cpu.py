@@ -86,7 +86,7 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2])
+@pytest.mark.parametrize("world", [2, 4])
 def test_sharding_plumbing_gloo(world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
