@@ -172,3 +172,21 @@ def test_python_key_text_format_matches_cpp(lib):
     with pytest.raises(KeyError):
         back.get("nope")
     assert PicklableMap.parse("a:1:2|b:3", "|", ":").toString() == "a:1:2|b:3"
+
+
+def test_missing_library_fails_loudly():
+    """No CPU fallback: without the CUDA library every entry point of the package raises."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "import cuhe_b200 as ch\n"
+            "try:\n"
+            "    ch.setParameters(5, 2, 1, 61, 20, 8191)\n"
+            "except Exception as e:\n"
+            "    print('RAISED', type(e).__name__, e)\n"
+            "else:\n"
+            "    print('NO ERROR')\n") % ROOT
+    env = dict(os.environ, CUHE_B200_LIB="/nonexistent/libcuhe_b200.so")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert "RAISED" in r.stdout and "NO ERROR" not in r.stdout, r.stdout + r.stderr
+    assert "libcuhe_b200" in r.stdout
