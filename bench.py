@@ -145,54 +145,77 @@ def _host_threads() -> int:
 
 
 def _cpu_setup():
+    """Two CPU restatements of the same multiply, both in oracle/ (test infrastructure):
+      * zzx  -- the reference's own host path, `t = a*b; t %= polyMod; coeffReduce` (examples/DHS/DHS.cu:219-221),
+                on the GMP runtime NTL is built on (oracle/zzx_gmp.c): one polynomial product per thread;
+      * ntt  -- the C port of the GPU pipeline (oracle/coracle.c), OpenMP over (polynomial, residue) pairs.
+    The faster one (zzx, ~10x) is what `cpu_baseline` and `--impl reference` report; NTL itself is absent."""
     from oracle.oracle import Oracle, lib
-    lib().orc_set_threads(C.c_int(_host_threads()))
+    threads = _host_threads()
+    lib().orc_set_threads(C.c_int(threads))
     o = Oracle(*WORKLOAD)
     o.barrett_tables()
+    o.inverse_series()
     rng = random.Random(1)
     q0 = o.moduli[0]
     polys = [o.to_raw([rng.randrange(q0) for _ in range(o.n)], 0) for _ in range(3)]
-    a = np.stack([polys[i % 3] for i in range(CPU_BATCH)])
-    b = np.stack([polys[(i + 1) % 3] for i in range(CPU_BATCH)])
-    return o, a, b, lib().orc_max_threads()
+
+    def operands(batch):
+        return (np.stack([polys[i % 3] for i in range(batch)]), np.stack([polys[(i + 1) % 3] for i in range(batch)]))
+    return o, operands, lib().orc_max_threads()
 
 
-def cpu_mul_rate(min_seconds: float, max_steps: int = 40):
-    """The oracle port on the box's host cores (OpenMP over every (polynomial, residue) pair)."""
-    o, a, b, cores = _cpu_setup()
-    o.mul_raw_batch(a, b, 0)                        # warm-up (page in, build tables)
+def _rate(fn, batch, min_seconds, max_steps):
+    fn()                                            # warm-up (page in, build tables)
     done, t0 = 0, time.perf_counter()
     while True:
-        o.mul_raw_batch(a, b, 0)
+        fn()
         done += 1
         el = time.perf_counter() - t0
         if el >= min_seconds or done >= max_steps:
             break
-    return CPU_BATCH * done / el, CPU_BATCH * done, el, cores
+    return batch * done / el, batch * done, el
+
+
+def cpu_mul_rate(min_seconds: float, max_steps: int = 40):
+    """Both CPU arms on the box's host cores; returns the cpu_baseline object of the JSON line."""
+    o, operands, cores = _cpu_setup()
+    za, zb = operands(cores)                        # one product per thread
+    v, done, el = _rate(lambda: o.mul_raw_batch_zzx(za, zb, 0), cores, min_seconds, max_steps)
+    na, nb = operands(CPU_BATCH)
+    v2, done2, el2 = _rate(lambda: o.mul_raw_batch(na, nb, 0), CPU_BATCH, min_seconds / 3, max_steps)
+    return {"value": v, "unit": "mul/s", "cores": cores, "kind": "port",
+            "sample": f"{done} multiplications of the same workload in {el:.1f} s: the reference's NTL host path "
+                      "(t = a*b; t %= Phi_m; coefficients mod q) restated on GMP (Kronecker product + inverse-series "
+                      "division), one product per thread; NTL itself is not installed",
+            "ntt_port": {"value": v2, "unit": "mul/s",
+                         "sample": f"{done2} multiplications in {el2:.1f} s: C port of the NTT pipeline, OpenMP over "
+                                   f"(polynomial, residue) pairs, batches of {CPU_BATCH}"}}
 
 
 def run_reference(args):
     """--impl reference: the reference's own CPU path is NTL's ZZX arithmetic (absent here and on the GPU
-    box); this arm times the C oracle port of the same pipeline with all host threads."""
+    box); this arm times its restatement on GMP (oracle/zzx_gmp.c) with one product per host thread."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    o, a, b, cores = _cpu_setup()
+    o, operands, cores = _cpu_setup()
+    a, b = operands(cores)
     for _ in range(max(1, min(args.warmup, 3))):
-        o.mul_raw_batch(a, b, 0)
+        o.mul_raw_batch_zzx(a, b, 0)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        o.mul_raw_batch(a, b, 0)
+        o.mul_raw_batch_zzx(a, b, 0)
     el = time.perf_counter() - t0
-    val = CPU_BATCH * args.steps / el
+    val = cores * args.steps / el
     out = {
         "impl": "reference", "metric": "homomorphic ctxt x ctxt mul/s", "value": val, "unit": "mul/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (mod 2^64-2^32+1) / u32 residues",
-        "data": "synthetic", "config": {"workload": WORKLOAD_NAME, "batch": CPU_BATCH},
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "big integers (GMP), exact",
+        "data": "synthetic", "config": {"workload": WORKLOAD_NAME, "batch": cores},
         "cpu_baseline": {"value": val, "unit": "mul/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps of {CPU_BATCH} multiplications, OpenMP over (polynomial, residue) pairs; "
-                                   "NTL (the reference's CPU path) is not installed"},
+                         "sample": f"{args.steps} steps of {cores} multiplications (one per thread): the reference's NTL host path "
+                                   "(examples/DHS/DHS.cu:219-221) restated on GMP; NTL itself is not installed"},
         "e2e": {"value": val, "unit": "mul/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -435,10 +458,7 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        v, done, el, cores = cpu_mul_rate(12.0)
-        cpu = {"value": v, "unit": "mul/s", "cores": cores, "kind": "port",
-               "sample": f"{done} multiplications of the same workload in {el:.1f} s (C oracle, OpenMP over "
-                         f"(polynomial, residue) pairs, batches of {CPU_BATCH})"}
+        cpu = cpu_mul_rate(12.0)
 
     if rank == 0:
         out = {

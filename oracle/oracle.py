@@ -23,10 +23,10 @@ _LIB = None
 
 
 def build() -> str:
-    """Compile coracle.c (building the checker is not using it)."""
+    """Compile coracle.c + zzx_gmp.c (building the checker is not using it)."""
     out = os.path.join(_HERE, "_build", "libcoracle.so")
-    src = os.path.join(_HERE, "coracle.c")
-    if (not os.path.exists(out)) or os.path.getmtime(out) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("coracle.c", "zzx_gmp.c", "Makefile")]
+    if (not os.path.exists(out)) or os.path.getmtime(out) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return out
 
@@ -43,6 +43,7 @@ def lib():
         _LIB.orc_ls_modP.restype = C.c_uint64
         _LIB.orc_ls_modP.argtypes = [C.c_uint64, C.c_int]
         _LIB.orc_max_threads.restype = C.c_int
+        _LIB.zzx_mul_mod_batch.restype = C.c_int
     return _LIB
 
 
@@ -320,6 +321,38 @@ class Oracle:
             _p(out), _p(a_raw), _p(b_raw), C.c_int(batch), C.c_int(L), C.c_int(W), C.c_int(Wp), C.c_int(self.N),
             C.c_int(self.H), C.c_int(self.n), _p(self.primes_np), _p(t["u_ntt"]), _p(t["m_ntt"]), _p(t["m_crt"]),
             _p(_roots(self.N)), _p(ic.q), _p(np.ascontiguousarray(ic.qp)), _p(ic.qpinv))
+        return out
+
+    def inverse_series(self) -> np.ndarray:
+        """rev(Phi)^-1 mod x^(m-n) over Z (Phi monic => integer coefficients; small for cyclotomic Phi,
+        where it is -(x^m - 1)/Phi up to the truncation).  int64[m-n]."""
+        if getattr(self, "_invser", None) is None:
+            n, d = self.n, self.par.mSize - self.n
+            rev = np.array(self.phi[::-1], dtype=np.int64)               # rev[0] = 1
+            inv = np.zeros(d, dtype=np.int64)
+            inv[0] = 1
+            for k in range(1, d):
+                j = min(k, n)
+                inv[k] = -int(np.dot(rev[1:j + 1], inv[k - 1::-1][:j] if k - 1 >= 0 else inv[:0]))
+            assert np.abs(inv).max() < 2**31, "inverse series is not small: not a cyclotomic modulus?"
+            self._invser = inv
+        return self._invser
+
+    def mul_raw_batch_zzx(self, a_raw: np.ndarray, b_raw: np.ndarray, lvl: int) -> np.ndarray:
+        """The reference's NTL host path (t = a*b; t %= polyMod; coeffReduce -- examples/DHS/DHS.cu:219-221)
+        restated on GMP (oracle/zzx_gmp.c): Kronecker product, division by Phi_m through the inverse
+        series, coefficients mod q_lvl; one product per OpenMP thread.  RAW in / RAW out like mul_raw_batch."""
+        W = self.W(lvl)
+        a_raw = np.ascontiguousarray(a_raw, dtype=np.uint32)
+        b_raw = np.ascontiguousarray(b_raw, dtype=np.uint32)
+        assert a_raw.shape[1:] == (self.H, W) and a_raw.shape == b_raw.shape
+        out = np.zeros_like(a_raw)
+        phi = np.array(self.phi, dtype=np.int64)
+        qw = np.ascontiguousarray(po.words_from_zz(self.moduli[lvl], W), dtype=np.uint32)
+        rc = lib().zzx_mul_mod_batch(_p(out), _p(a_raw), _p(b_raw), C.c_int(a_raw.shape[0]), C.c_int(self.H), C.c_int(W),
+                                     C.c_int(self.n), C.c_int(self.par.mSize), _p(phi), _p(self.inverse_series()), _p(qw))
+        if rc != 0:
+            raise RuntimeError("libgmp.so.10 could not be loaded for the GMP CPU path")
         return out
 
     def mul_exact(self, a: Sequence[int], b: Sequence[int], lvl: int) -> List[int]:

@@ -199,3 +199,28 @@ def test_golden_fixtures():
         got = compute_case(case["params"], case["seed"], exact=False)
         for k in ("crt_sha", "ntt_sha", "mul_crt_sha", "mul_raw_sha", "modswitch_sha"):
             assert got[k] == case[k], (case["name"], k)
+
+
+@pytest.mark.parametrize("ps", [SIMPLE_DHS, (4, 2, 16, 50, 25, 21845)], ids=["m8191_prime", "m21845_composite"])
+def test_gmp_zzx_path_equals_ntt_pipeline(ps):
+    """oracle/zzx_gmp.c -- the reference's NTL host path (t = a*b; t %= polyMod; coeffReduce,
+    examples/DHS/DHS.cu:219-221) restated on GMP, bench.py's CPU arm -- gives, word for word, what the
+    CRT/NTT/Barrett/ICRT pipeline gives, and what exact big-integer ring arithmetic gives."""
+    o = get_oracle(ps)
+    W, H, n = o.W(0), o.H, o.n
+    rng = np.random.default_rng(11)
+    top_bits = o.moduli[0].bit_length() - 1 - 32 * (W - 1)
+
+    def polys(batch):
+        x = rng.integers(0, 1 << 32, size=(batch, H, W), dtype=np.uint32)
+        x[:, :, W - 1] &= np.uint32((1 << top_bits) - 1)
+        x[:, n:, :] = 0
+        return x
+    a, b = polys(3), polys(3)
+    a[2, :n] = np.array(po.words_from_zz(o.moduli[0] - 1, W), dtype=np.uint32)      # maximal coefficients
+    b[2, :n] = a[2, :n]
+    got = o.mul_raw_batch_zzx(a, b, 0)
+    assert np.array_equal(got, o.mul_raw_batch(a, b, 0))
+    assert o.from_raw(got[0]) == o.mul_exact(o.from_raw(a[0]), o.from_raw(b[0]), 0)
+    inv = o.inverse_series()
+    assert len(inv) == o.par.mSize - n and int(np.abs(inv).max()) <= 2
