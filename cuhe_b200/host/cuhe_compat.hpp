@@ -79,34 +79,25 @@ public:
     virtual ~CuPolynomial();
     void reset();                                           // idempotent (explicit destructor calls in Prince.cu)
 
-    void logq(int val);
-    void domain(int val);
-    void device(int val);
-    void isProd(bool val);
-    void zRep(ZZX val);
-    void rRep(uint32* val);
-    void cRep(uint32* val);
-    void nRep(uint64* val);
-    int logq();
-    int domain();
-    int device();
-    bool isProd();
-    ZZX zRep();
-    uint32* rRep();
-    uint32* cRep();
-    uint64* nRep();
+    // state: setter / getter pairs (the reference overloads one name for both)
+    void logq(int val);      int logq();
+    void domain(int val);    int domain();
+    void device(int val);    int device();
+    void isProd(bool val);   bool isProd();
+    // representations: host value, RAW, CRT, NTT (raw pointer hand-offs, as in the reference)
+    void zRep(ZZX val);      ZZX zRep();
+    void rRep(uint32* val);  uint32* rRep();
+    void cRep(uint32* val);  uint32* cRep();
+    void nRep(uint64* val);  uint64* nRep();
 
-    void x2z(cudaStream_t st = 0);
-    void x2r(cudaStream_t st = 0);
-    void x2c(cudaStream_t st = 0);
-    void x2n(cudaStream_t st = 0);
+    // conversions to the named domain from whatever the current one is
+    void x2z(cudaStream_t st = 0);  void x2r(cudaStream_t st = 0);
+    void x2c(cudaStream_t st = 0);  void x2n(cudaStream_t st = 0);
 
-    void rRepCreate(cudaStream_t st = 0);
-    void cRepCreate(cudaStream_t st = 0);
-    void nRepCreate(cudaStream_t st = 0);
-    void rRepFree();
-    void cRepFree();
-    void nRepFree();
+    // device buffers of each representation
+    void rRepCreate(cudaStream_t st = 0);  void rRepFree();
+    void cRepCreate(cudaStream_t st = 0);  void cRepFree();
+    void nRepCreate(cudaStream_t st = 0);  void nRepFree();
 
     int coeffWords();
     size_t rRepSize();
@@ -114,12 +105,10 @@ public:
     virtual size_t nRepSize() = 0;
 
 protected:
-    void z2r(cudaStream_t st = 0);
-    void r2z(cudaStream_t st = 0);
-    void r2c(cudaStream_t st = 0);
-    void c2r(cudaStream_t st = 0);
-    void c2n(cudaStream_t st = 0);
-    void n2c(cudaStream_t st = 0);
+    // single steps of the domain chain ZZX <-> RAW <-> CRT <-> NTT
+    void z2r(cudaStream_t st = 0);  void r2z(cudaStream_t st = 0);
+    void r2c(cudaStream_t st = 0);  void c2r(cudaStream_t st = 0);
+    void c2n(cudaStream_t st = 0);  void n2c(cudaStream_t st = 0);
     virtual int levelForKernels();                          // level of the residue set (-1: plaintext)
     void assignFrom(const CuPolynomial& other);
 
@@ -142,14 +131,12 @@ public:
     CuCtxt() : CuPolynomial() { level_ = -1; }
     CuCtxt(const CuCtxt& other) : CuPolynomial(other) { level_ = other.level_; }
     CuCtxt& operator=(const CuCtxt& other) { CuPolynomial::operator=(other); level_ = other.level_; return *this; }
-    void setLevel(int lvl, int dom, int dev, cudaStream_t st = 0);
-    void setLevel(int lvl, int dev, ZZX val);
     int level();
-    void modSwitch(cudaStream_t st = 0);
-    void modSwitch(int lvl, cudaStream_t st = 0);
+    void setLevel(int lvl, int dev, ZZX val);                          // from a host value
+    void setLevel(int lvl, int dom, int dev, cudaStream_t st = 0);     // empty buffers in domain `dom`
     void relin(cudaStream_t st = 0);
-    size_t cRepSize();
-    size_t nRepSize();
+    void modSwitch(cudaStream_t st = 0);  void modSwitch(int lvl, cudaStream_t st = 0);
+    size_t cRepSize();  size_t nRepSize();
 
 protected:
     int levelForKernels() { return level_; }
@@ -158,21 +145,24 @@ protected:
 
 class CuPtxt : public CuPolynomial {
 public:
-    void setLogq(int logq, int dom, int dev, cudaStream_t st = 0);
     void setLogq(int logq, int dev, ZZX val);
-    size_t cRepSize();
-    size_t nRepSize();
+    void setLogq(int logq, int dom, int dev, cudaStream_t st = 0);
+    size_t cRepSize();  size_t nRepSize();
 };
 
 // ---- operations (cuhe/CuHE.h:178-208) -----------------------------------------------------------
-void mulZZX(ZZX& x, ZZX a, ZZX b, int lvl, int dev, cudaStream_t st = 0);
-void copy(CuCtxt& x, CuCtxt a, cudaStream_t st = 0);
+// ciphertext x ciphertext / ciphertext x plaintext, NTT domain in, product flagged isProd
 void cAnd(CuCtxt& x, CuCtxt& a, CuCtxt& b, cudaStream_t st = 0);
 void cAnd(CuCtxt& x, CuCtxt& c, CuPtxt& p, cudaStream_t st = 0);
+// sums in the CRT or NTT domain; cNot adds modMsg - 1 to coefficient 0 (CRT domain)
 void cXor(CuCtxt& x, CuCtxt& a, CuCtxt& b, cudaStream_t st = 0);
 void cXor(CuCtxt& x, CuCtxt& c, CuPtxt& p, cudaStream_t st = 0);
 void cNot(CuCtxt& x, CuCtxt& a, cudaStream_t st = 0);
-void moveTo(CuCtxt& x, int dstDev, cudaStream_t st = 0);
+// copies within and across devices
+void copy(CuCtxt& x, CuCtxt a, cudaStream_t st = 0);
 void copyTo(CuCtxt& dst, CuCtxt& src, int dstDev, cudaStream_t st = 0);
+void moveTo(CuCtxt& x, int dstDev, cudaStream_t st = 0);
+// whole host-to-host product: (a * b mod Phi_m) mod q_lvl
+void mulZZX(ZZX& x, ZZX a, ZZX b, int lvl, int dev, cudaStream_t st = 0);
 
 }  // namespace cuHE
