@@ -4,12 +4,13 @@ They mirror the semantics of the reference's own tests:
 tests/test_ModP.cu (primitives), tests/test_ntt.cu (ext-NTT == DFT) and the
 domain machine exercised by examples/DHS/simple_DHS.cu."""
 import ctypes as C
+import os
 import random
 
 import numpy as np
 import pytest
 
-from common import C2, MID32K, MID64K, SIMPLE_DHS, SMALL_RELIN, get_oracle
+from common import C2, MID32K, MID64K, ROOT, SIMPLE_DHS, SMALL_RELIN, get_oracle
 
 pytestmark = pytest.mark.gpu
 
@@ -580,3 +581,30 @@ def test_modp_canonical_residue(eng16):
     dx = eng16.up(x)
     eng16.call("cuhe_modp_batch", 5, p(out), p(dx), None, C.c_size_t(x.size), 0, eng16.st())
     assert np.array_equal(Eng.dn(out, np.uint64).astype(object), x.astype(object) % P)
+
+
+@pytest.mark.xfail(strict=False, reason="added after this round's GPU minutes were spent: first on-GPU run pending")
+def test_modp_primitives_equal_the_reference_header(eng16):
+    """Differential test against the REFERENCE's own device code: oracle/_ref/libref_modp.so wraps
+    _add/_sub/_mul/_ls_modP of cuhe/ModP.h (compiled for sm_100a from the reference tree by oracle/Makefile,
+    target `ref`).  Inputs follow tests/test_ModP.cu:38-49; shifts are the l = 3*a*b the reference supports."""
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_modp.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_modp.so was not built (no reference tree at build time)")
+    ref = C.CDLL(path)
+    ref.ref_modp_batch.restype = C.c_int
+    ref.ref_modp_batch.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+    x, y = _modp_inputs(1 << 18, 77)
+    dx, dy = eng16.up(x), eng16.up(y)
+    ours, theirs = eng16.empty(x.shape, np.uint64), eng16.empty(x.shape, np.uint64)
+    torch = eng16.torch
+    for op in (0, 1, 2):
+        eng16.call("cuhe_modp_batch", op, p(ours), p(dx), p(dy), C.c_size_t(x.size), 0, eng16.st())
+        assert ref.ref_modp_batch(op, p(theirs), p(dx), p(dy), x.size, 0, eng16.st()) == 0
+        torch.cuda.synchronize()
+        assert torch.equal(ours, theirs), f"op {op}"
+    for l in sorted({3 * a * b for a in range(8) for b in range(8)}):
+        eng16.call("cuhe_modp_batch", 3, p(ours), p(dx), None, C.c_size_t(x.size), l, eng16.st())
+        assert ref.ref_modp_batch(3, p(theirs), p(dx), None, x.size, l, eng16.st()) == 0
+        torch.cuda.synchronize()
+        assert torch.equal(ours, theirs), f"shift {l}"
