@@ -190,3 +190,26 @@ def test_missing_library_fails_loudly():
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
     assert "RAISED" in r.stdout and "NO ERROR" not in r.stdout, r.stdout + r.stderr
     assert "libcuhe_b200" in r.stdout
+
+
+def test_cpp_bigint_stand_in_against_python_integers(lib):
+    """cuhe_b200/host/zz_lite.hpp (used when NTL is not installed): +, -, *, % (result in [0, m)), NumBits,
+    byte import/export and comparisons equal Python integers on 300 random and edge operands."""
+    import random
+    import subprocess
+    exe = _build_cpp_compat_test("zz_test")
+    rng = random.Random(5)
+    cases = [(0, 0, 1), (1, -1, 2), (-5, 3, 7), (2**64, 2**64 - 1, 2**32), (-(2**200), 2**199 + 1, 10**9 + 7),
+             (10**9, 10**9, 10**9), (10**18 - 1, 1, 10**9)]
+    for _ in range(300):
+        ba, bb, bm = rng.choice([1, 31, 32, 33, 63, 64, 65, 576, 1152, 2000]), rng.randrange(1, 1200), rng.randrange(1, 700)
+        a, b = rng.getrandbits(ba) * rng.choice([1, -1]), rng.getrandbits(bb) * rng.choice([1, -1])
+        cases.append((a, b, rng.getrandbits(bm) + 1))
+    text = "".join(f"{a} {b} {m}\n" for a, b, m in cases)
+    r = subprocess.run([exe], input=text, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().split("\n")
+    assert len(lines) == len(cases)
+    for (a, b, m), line in zip(cases, lines):
+        want = f"{a + b} {a - b} {a * b} {a % m} {abs(a).bit_length()} {abs(a)} {1 if a < b else 0}{1 if a == b else 0}"
+        assert line == want, (a, b, m)
