@@ -5,6 +5,8 @@ import ctypes as C
 import os
 import re
 
+import numpy as np
+
 import pytest
 
 from common import C2, PRINCE, ROOT, SIMPLE_DHS, SMALL_RELIN, MID32K, MID64K
@@ -213,3 +215,23 @@ def test_cpp_bigint_stand_in_against_python_integers(lib):
     for (a, b, m), line in zip(cases, lines):
         want = f"{a + b} {a - b} {a * b} {a % m} {abs(a).bit_length()} {abs(a)} {1 if a < b else 0}{1 if a == b else 0}"
         assert line == want, (a, b, m)
+
+
+def test_host_marshalling_equals_oracle_layout(lib):
+    """z2r / r2z host halves of the Python mirror (cuhe/CuHE.cu:317-348: BytesFromZZ / ZZFromBytes per
+    coefficient): RAW u32[rawLen][words], little-endian words, zero beyond the polynomial."""
+    import random
+    from cuhe_b200.api import _raw_np_to_zzx, _zzx_to_raw_np
+    from common import get_oracle
+    o = get_oracle(SMALL_RELIN)
+    rng = random.Random(2)
+    for lvl in (0, o.par.depth - 1):
+        W = o.W(lvl)
+        coeffs = [rng.randrange(o.moduli[lvl]) for _ in range(o.n)]
+        coeffs[0], coeffs[1], coeffs[-1] = 0, o.moduli[lvl] - 1, 1
+        raw = _zzx_to_raw_np(coeffs, W, o.H)
+        assert raw.shape == (o.H, W) and raw.dtype == np.uint32
+        assert np.array_equal(raw, o.to_raw(coeffs, lvl))
+        assert _raw_np_to_zzx(raw, o.n) == coeffs
+    short = _zzx_to_raw_np([5, 6], 2, o.H)                      # a short ZZX is zero-extended
+    assert short[0, 0] == 5 and short[1, 0] == 6 and not short[2:].any()
