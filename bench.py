@@ -272,8 +272,32 @@ def run_ours(args):
     st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)  # noqa: E731
     p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
 
+    # CUHE_B200_OVERLAP=1 (multi-GPU, not measured yet, off by default): the batch is processed as two halves
+    # on two streams, so that the collectives of one half run under the kernels of the other
+    overlap = world > 1 and os.environ.get("CUHE_B200_OVERLAP") == "1" and B >= 2
+    if overlap:
+        halves = [(0, B // 2), (B // 2, B)]
+        side = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+
+    def step_overlapped(k):
+        cur = torch.cuda.current_stream()
+        outs = []
+        for s_, (lo_, up_) in zip(side, halves):
+            s_.wait_stream(cur)
+            with torch.cuda.stream(s_):
+                nb = up_ - lo_
+                check(lib.cuhe_mul_crt_batch(h, p(crt_loc[lo_:up_]), p(a_dev[k][lo_:up_]), p(b_dev[k][lo_:up_]), 0, nb, st()))
+                crt_slice = sh.exchange_for_icrt(crt_loc[lo_:up_], L, rank, world)
+                check(lib.cuhe_icrt_slice_batch(h, p(raw_slice[lo_:up_]), p(crt_slice), 0, cb, ce - cb, nb, st()))
+                outs.append(sh.all_gather_raw_slices(raw_slice[lo_:up_], world))
+        for s_ in side:
+            cur.wait_stream(s_)
+        return outs
+
     def step(i):
         k = i % NBUF
+        if overlap:
+            return step_overlapped(k)
         check(lib.cuhe_mul_crt_batch(h, p(crt_loc), p(a_dev[k]), p(b_dev[k]), 0, B, st()))
         if world == 1:
             check(lib.cuhe_icrt_batch(h, p(raw_out), p(crt_loc), 0, 0, H, B, st()))
