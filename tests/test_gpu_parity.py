@@ -608,3 +608,48 @@ def test_modp_primitives_equal_the_reference_header(eng16):
         assert ref.ref_modp_batch(3, p(theirs), p(dx), None, x.size, l, eng16.st()) == 0
         torch.cuda.synchronize()
         assert torch.equal(ours, theirs), f"shift {l}"
+
+
+@pytest.mark.xfail(strict=False, reason="added after this round's GPU minutes were spent: first on-GPU run pending")
+def test_gpu_outputs_match_the_committed_golden_fixtures(lib):
+    """The GPU path against tests/golden/golden.json directly (no oracle call on this side): SHA-256 of cRep,
+    nRep, product cRep, product rRep and the modswitch output for the seeded inputs of make_golden.py, whose
+    products were verified against exact big-integer ring arithmetic when the fixtures were written --
+    including the full BASELINE size (24 primes, N = 65536)."""
+    import hashlib
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(ROOT, "tests", "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))["cases"]
+
+    def sha(t, dt):
+        return hashlib.sha256(np.ascontiguousarray(Eng.dn(t, dt)).tobytes()).hexdigest()
+    for case in gold:
+        e = Eng(lib, tuple(case["params"]))
+        try:
+            o = e.orc                                           # only for sizes and the seeded inputs
+            a, b = mg.inputs(o, case["seed"])
+            ra, rb = o.to_raw(a, 0), o.to_raw(b, 0)
+            L, H, N, W = o.L(0), o.H, o.N, o.W(0)
+            d_ra, d_rb = e.up(ra), e.up(rb)
+            d_crt = e.empty((L, H), np.uint32)
+            e.call("cuhe_crt", p(d_crt), p(d_ra), 0, e.st())
+            assert sha(d_crt, np.uint32) == case["crt_sha"], case["name"]
+            d_ntt = e.empty((L, N), np.uint64)
+            e.call("cuhe_ntt", p(d_ntt), p(d_crt), 0, e.st())
+            assert sha(d_ntt, np.uint64) == case["ntt_sha"], case["name"]
+            d_mc = e.empty((1, L, H), np.uint32)
+            e.call("cuhe_mul_crt_batch", p(d_mc), p(d_ra), p(d_rb), 0, 1, e.st())
+            assert sha(d_mc, np.uint32) == case["mul_crt_sha"], case["name"]
+            d_mr = e.empty((H, W), np.uint32)
+            e.call("cuhe_icrt", p(d_mr), p(d_mc), 0, 0, H, e.st())
+            assert sha(d_mr, np.uint32) == case["mul_raw_sha"], case["name"]
+            if case["modswitch_sha"]:
+                d_ms = d_mc[0].clone()
+                e.call("cuhe_mod_switch", p(d_ms), p(d_ms), p(d_ms[L - 1]), 0, e.st())
+                assert hashlib.sha256(np.ascontiguousarray(Eng.dn(d_ms, np.uint32)[: L - 1]).tobytes()).hexdigest() \
+                    == case["modswitch_sha"], case["name"]
+        finally:
+            e.close()
