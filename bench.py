@@ -484,6 +484,18 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_mul_rate(12.0)
 
+    sweep = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        # the table the reference publishes (doc/Perf_NTT.txt): per-transform time for N x batch, and the
+        # configs[0] latency.  Isolated in a child process so that nothing it does can disturb this line.
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ntt_bench.py"), "--sweep"],
+                               capture_output=True, text=True, timeout=180)
+            lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            sweep = json.loads(lines[-1]) if lines else {"error": (r.stderr or "no output")[-300:]}
+        except Exception as ex:                                  # noqa: BLE001
+            sweep = {"error": repr(ex)[:300]}
+
     if rank == 0:
         out = {
             "metric": "homomorphic ctxt x ctxt mul/s", "value": value, "unit": "mul/s", "n_gpus": world,
@@ -492,7 +504,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD_NAME, "batch": B, "batch_per_gpu": args.batch, "parallelism": f"residue-shard x{world}" if world > 1 else "single GPU",
                        "l2": f"{NBUF} rotating operand sets; per-step NTT intermediates {2 * B * L * N * 8 / 1e6:.0f} MB exceed the 126 MB L2"},
-            "ntt_64k_per_s": ntt_rate, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "ntt_64k_per_s": ntt_rate, "ntt_sweep": sweep, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": clocks,
         }
         print(json.dumps(out))
