@@ -484,17 +484,21 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_mul_rate(12.0)
 
-    sweep = None
+    def child_json(script, *cli):
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", script), *cli], capture_output=True, text=True, timeout=180)
+            lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            return json.loads(lines[-1]) if lines else {"error": (r.stderr or "no output")[-300:]}
+        except Exception as ex:                                  # noqa: BLE001
+            return {"error": repr(ex)[:300]}
+
+    sweep = relin3 = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        # BASELINE configs[2]: key switch at N = 65536, 44 primes, 66 keys (1.52 GB resident), tools/relin_bench.py
+        relin3 = child_json("relin_bench.py")
         # the table the reference publishes (doc/Perf_NTT.txt): per-transform time for N x batch, and the
         # configs[0] latency.  Isolated in a child process so that nothing it does can disturb this line.
-        try:
-            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ntt_bench.py"), "--sweep"],
-                               capture_output=True, text=True, timeout=180)
-            lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
-            sweep = json.loads(lines[-1]) if lines else {"error": (r.stderr or "no output")[-300:]}
-        except Exception as ex:                                  # noqa: BLE001
-            sweep = {"error": repr(ex)[:300]}
+        sweep = child_json("ntt_bench.py", "--sweep")
 
     if rank == 0:
         out = {
@@ -504,7 +508,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD_NAME, "batch": B, "batch_per_gpu": args.batch, "parallelism": f"residue-shard x{world}" if world > 1 else "single GPU",
                        "l2": f"{NBUF} rotating operand sets; per-step NTT intermediates {2 * B * L * N * 8 / 1e6:.0f} MB exceed the 126 MB L2"},
-            "ntt_64k_per_s": ntt_rate, "ntt_sweep": sweep, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "ntt_64k_per_s": ntt_rate, "ntt_sweep": sweep, "relin_config3": relin3, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": clocks,
         }
         print(json.dumps(out))
