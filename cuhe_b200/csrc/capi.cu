@@ -894,7 +894,12 @@ int cuhe_relin(cuhe_ctx* c, uint64_t* dst, const uint32_t* raw, int lvl, cuhe_st
         static const int mac_un = [] { const char* e = getenv("CUHE_B200_RELIN_UNROLL"); return e ? atoi(e) : 2; }();
         const long long ks = N, ps = (long long)K0 * N;
         uint64_t* Dp = D.as<uint64_t>();
-        if (mac_rb == 1) {
+        static const bool mac_ring = getenv("CUHE_B200_RELIN_RING") != nullptr;   // generation 3, not yet measured
+        if (mac_ring) {
+            constexpr int RB = 2, S = 8;
+            dim3 grid(N / 2 / 128, (rows + RB - 1) / RB);
+            relin_mac_kernel_ring<RB, S><<<grid, 128, (size_t)S * (RB + 1) * 128 * 16, st>>>(dst, Dp, c->d_ek, K, ks, ps, 0, 1, N, rows);
+        } else if (mac_rb == 1) {
             dim3 grid((N + 255) / 256, rows);
             relin_mac_kernel<<<grid, 256, 0, st>>>(dst, Dp, c->d_ek, K, ks, ps, 0, 1, N);
         } else {
