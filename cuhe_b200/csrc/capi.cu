@@ -82,11 +82,6 @@ struct cuhe_ctx {
     uint32_t* d_m_crt = nullptr;
     // fast reduction modulo Phi_m (needs Phi | x^m - 1): quotient through an Nq-point product,
     // q*Phi through an Nr-point product; tables for the local rows of level 0
-    // both NTT passes in one persistent thread-block-cluster launch (CUHE_B200_NTT_FUSED=1).  Off by
-    // default: measured 17 % slower than two launches on B200 (1.13 M vs 1.36 M 64K transforms/s) --
-    // the two cluster barriers per transform cost more than the saved DRAM round trip, which the
-    // ALU-bound kernels were not waiting for anyway.
-    bool use_fused = false;
     bool fast_reduce = false;
     int Nq = 0, Nr = 0, k1 = 0;            // k1 = m - n quotient coefficients
     uint64_t *d_tq = nullptr, *d_tr = nullptr;
@@ -154,45 +149,14 @@ static const NttPlan& get_plan(cuhe_ctx* c, int N) {
 }
 
 // ---- transform drivers -------------------------------------------------------
-// Runs pass 1 + pass 2 for `count` transforms.  Fused path: one launch of persistent thread-block
-// clusters whose N-word intermediates live in a small reused (L2-resident) slot array; split path:
-// two launches through a count*N-word scratch.  a.scratch / b.scratch are filled in here.
+// Runs pass 1 + pass 2 for `count` transforms through a count*N-word scratch (a.scratch / b.scratch are filled in
+// here).  Measured and dropped in round 2 (profiles/r02_ntt_chunk_sweep.txt): running the two passes over chunks of
+// 16-128 transforms through an L2-sized scratch removes the intermediate's DRAM round trip but is 11-60 % slower
+// (launches of 1-2 waves), and the one-launch cluster variant of round 1 was 17 % slower.
 static void run_ntt(cuhe_ctx* c, const NttPlan& pl, int mode, int out, Pass1Args a, Pass2Args b, int count,
                     cudaStream_t st) {
     if (count <= 0) return;
-    if (c->use_fused) {
-        Tmp slots(c, (size_t)fused_slots(pl.r3) * pl.N * 8, st);
-        a.scratch = slots.as<uint64_t>(); b.scratch = slots.as<uint64_t>();
-        cudaError_t e = launch_fused(pl.r3, mode, out, a, b, count, st);
-        if (e == cudaSuccess) return;
-        if (e != cudaErrorNotSupported) throw CudaFail{e, "launch_fused", __LINE__};
-        cudaGetLastError();
-    }
-    // CUHE_B200_NTT_CHUNK_ROWS=<rows> (opt-in, written after the last GPU run of round 1, not yet measured):
-    // run the two passes over chunks of that many transforms through ONE reused scratch, so that the pass-1
-    // output is still in L2 when pass 2 reads it and is overwritten there by the next chunk -- removes the
-    // intermediate's DRAM round trip (traffic 2.3x -> ~1x algorithmic) at the price of smaller launches.
-    // Chunks are multiples of row_mod, so every per-row table / prime index (t % row_mod) is unchanged.
-    static const int chunk_rows = [] { const char* e = getenv("CUHE_B200_NTT_CHUNK_ROWS"); return e ? atoi(e) : 0; }();
-    if (chunk_rows > 0 && count > chunk_rows) {
-        const int rm = std::max(1, std::max(a.row_mod, b.row_mod));
-        const int C = std::max(rm, chunk_rows / rm * rm);
-        Tmp scratch(c, (size_t)C * pl.N * 8, st);
-        const size_t in_es = (mode == IN_U64_REV || mode == IN_U64_REV_MUL) ? 8 : 4, out_es = (out == OUT_U32_MODP) ? 4 : 8;
-        for (int t0 = 0; t0 < count; t0 += C) {
-            const int cnt = std::min(C, count - t0);
-            Pass1Args a2 = a;
-            Pass2Args b2 = b;
-            a2.scratch = scratch.as<uint64_t>(); b2.scratch = scratch.as<uint64_t>();
-            if (mode == IN_DIGIT) a2.digit_first = a.digit_first + t0;
-            else a2.src = (const char*)a.src + (size_t)t0 * (size_t)a.src_stride * in_es;
-            if (a.src2) a2.src2 = (const char*)a.src2 + (size_t)t0 * (size_t)a.src2_stride * 8;
-            b2.dst = (char*)b.dst + (size_t)t0 * (size_t)b.dst_stride * out_es;
-            CK(launch_pass1(mode, a2, cnt, st));
-            CK(launch_pass2(pl.r3, out, b2, cnt, st));
-        }
-        return;
-    }
+    b.tw1 = a.tw1;                      // the pass-1 table is applied in the loads of pass 2
     Tmp scratch(c, (size_t)count * pl.N * 8, st);
     a.scratch = scratch.as<uint64_t>(); b.scratch = scratch.as<uint64_t>();
     CK(launch_pass1(mode, a, count, st));
@@ -515,7 +479,6 @@ int cuhe_ctx_create(cuhe_ctx** out, const cuhe_params* p, int device, int shard_
                     chk.logCrtPrime == p->logCrtPrime && chk.numEvalKey == p->numEvalKey,
                 "cuhe_params was not produced by cuhe_set_parameters");
         c->device = device; c->rank = shard_rank; c->world = shard_world;
-        { const char* sp = getenv("CUHE_B200_NTT_FUSED"); c->use_fused = (sp && sp[0] == '1'); }
         DeviceGuard dg(device);
         // pool: replaces DeviceAllocator (cuhe/DeviceManager.cu:36-138)
         cudaMemPoolProps props{};
@@ -919,12 +882,7 @@ int cuhe_relin(cuhe_ctx* c, uint64_t* dst, const uint32_t* raw, int lvl, cuhe_st
         static const int mac_un = [] { const char* e = getenv("CUHE_B200_RELIN_UNROLL"); return e ? atoi(e) : 2; }();
         const long long ks = N, ps = (long long)K0 * N;
         uint64_t* Dp = D.as<uint64_t>();
-        static const bool mac_ring = getenv("CUHE_B200_RELIN_RING") != nullptr;   // generation 3, not yet measured
-        if (mac_ring) {
-            constexpr int RB = 2, S = 8;
-            dim3 grid(N / 2 / 128, (rows + RB - 1) / RB);
-            relin_mac_kernel_ring<RB, S><<<grid, 128, (size_t)S * (RB + 1) * 128 * 16, st>>>(dst, Dp, c->d_ek, K, ks, ps, 0, 1, N, rows);
-        } else if (mac_rb == 1) {
+        if (mac_rb == 1) {
             dim3 grid((N + 255) / 256, rows);
             relin_mac_kernel<<<grid, 256, 0, st>>>(dst, Dp, c->d_ek, K, ks, ps, 0, 1, N);
         } else {

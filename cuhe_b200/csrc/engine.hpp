@@ -6,7 +6,7 @@
 
 namespace cuhe_b200 {
 
-// ---- NTT pass 1 / pass 2 arguments (kernels in ntt.cuh) --------------------
+// ---- NTT pass 1 / pass 2 arguments (kernels in ntt96.cuh) ------------------
 enum Pass1In {
     IN_EXT_U32 = 0,     // u32[N/2] zero-padded input                        (ntt_1_*_ext)
     IN_DIGIT = 1,       // w-bit window of multi-word raw coefficients        (ntt_1_*_ext_block)
@@ -20,7 +20,7 @@ struct Pass1Args {
     uint64_t* scratch;         // [count][N]
     const void* src;           // see Pass1In
     const void* src2;          // second operand for IN_U64_REV_MUL
-    const uint64_t* tw1;       // [64][N2]: w^(k1*j2) (times N^-1 for the inverse)
+    const uint64_t* tw1;       // handed on to pass 2 (Pass2Args::tw1) by the driver
     long long src_stride;      // elements between consecutive transforms
     long long src2_stride;
     int n2;                    // N / 64
@@ -40,6 +40,7 @@ struct Pass2Args {
     void* dst;                 // [count][dst_stride]
     const uint64_t* scratch;   // [count][N]
     const uint64_t* tw2;       // [64][R3]: w_N2^(k2a*j2b)
+    const uint64_t* tw1;       // [64][N2]: w^(k1*j2) (times N^-1 for the inverse), applied by the loads of pass 2
     const uint64_t* mul_tab;   // OUT_U64_MUL: [rows][N], row = t % row_mod
     const uint32_t* primes;    // OUT_U32_MODP: all primes
     const uint64_t* mus;       // floor(2^64/p)
@@ -49,11 +50,6 @@ struct Pass2Args {
 };
 cudaError_t launch_pass1(int mode, const Pass1Args& a, int count, cudaStream_t st);
 cudaError_t launch_pass2(int r3, int out, const Pass2Args& a, int count, cudaStream_t st);
-// both passes in one launch (persistent thread-block clusters, L2-resident intermediate).
-// a.scratch / b.scratch must point at `fused_slots(r3)` * N words.  Returns cudaErrorNotSupported for a
-// (mode, out) pair that is not instantiated.
-int fused_slots(int r3);
-cudaError_t launch_fused(int r3, int mode, int out, const Pass1Args& a, const Pass2Args& b, int count, cudaStream_t st);
 
 // which primes the rows of a [rows][..] array refer to
 struct PrimeView {

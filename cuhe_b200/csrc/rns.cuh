@@ -458,72 +458,4 @@ relin_mac_kernel_v2(uint64_t* __restrict__ dst, const uint64_t* __restrict__ D, 
     }
 }
 
-// Generation 3 (opt-in, CUHE_B200_RELIN_RING=1; written after the last GPU run of round 1, NOT yet measured or
-// parity-run on the GPU): same arithmetic as relin_mac_kernel_v2, but the key and digit values are staged
-// through a thread-private ring in shared memory filled S iterations ahead with cp.async (LDGSTS), so the
-// bytes in flight per SM no longer depend on registers: 4 CTAs x 8 stages x (RB + 1) x 2 KB = 192 KB against
-// ~57 KB for generation 2, whose top stall is long_scoreboard at 40 % occupancy.  Every thread reads back only
-// what it copied itself, so cp.async.wait_group is the only synchronisation needed.
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem)
-                 : "memory");
-}
-template <int RB, int S>
-__global__ void __launch_bounds__(128)
-relin_mac_kernel_ring(uint64_t* __restrict__ dst, const uint64_t* __restrict__ D, const uint64_t* __restrict__ ek,
-                      int K, long long ek_key_stride, long long ek_prime_stride, int prime_base, int prime_step, int N,
-                      int rows) {
-    extern __shared__ ulonglong2 ring[];                              // [S][RB + 1][128]
-    const int tid = threadIdx.x;
-    const int i = (blockIdx.x * blockDim.x + tid) * 2;
-    const int r0 = blockIdx.y * RB;
-    if (i >= N) return;
-    const ulonglong2* e[RB];
-#pragma unroll
-    for (int j = 0; j < RB; j++) {
-        const int r = min(r0 + j, rows - 1);
-        e[j] = reinterpret_cast<const ulonglong2*>(ek + (long long)(prime_base + prime_step * r) * ek_prime_stride + i);
-    }
-    const ulonglong2* d = reinterpret_cast<const ulonglong2*>(D + i);
-    const long long dstep = N / 2, estep = ek_key_stride / 2;
-    auto slot = [&](int stage, int j) -> ulonglong2* { return ring + ((size_t)stage * (RB + 1) + j) * 128 + tid; };
-    auto fill = [&](int k) {
-        if (k < K) {
-            const int stage = k % S;
-#pragma unroll
-            for (int j = 0; j < RB; j++) cp_async16(slot(stage, j), e[j] + (long long)k * estep);
-            cp_async16(slot(stage, RB), d + (long long)k * dstep);
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");          // one group per iteration, empty past the end
-    };
-#pragma unroll
-    for (int k = 0; k < S; k++) fill(k);
-    MacAcc acc[RB][2];
-#pragma unroll
-    for (int j = 0; j < RB; j++) { acc[j][0] = MacAcc{0, 0, 0, 0, 0, 0, 0, 0}; acc[j][1] = acc[j][0]; }
-    for (int k = 0; k < K; k++) {
-        asm volatile("cp.async.wait_group %0;" ::"n"(S - 1) : "memory");   // group k has landed
-        const int stage = k % S;
-        const ulonglong2 x = *slot(stage, RB);
-        ulonglong2 y[RB];
-#pragma unroll
-        for (int j = 0; j < RB; j++) y[j] = *slot(stage, j);
-        fill(k + S);                                                  // the slot is free again: refill it
-#pragma unroll
-        for (int j = 0; j < RB; j++) {
-            mac_wide(acc[j][0], x.x, y[j].x);
-            mac_wide(acc[j][1], x.y, y[j].y);
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < RB; j++) {
-        if (r0 + j < rows) {
-            ulonglong2 o;
-            o.x = mac_fold(acc[j][0]);
-            o.y = mac_fold(acc[j][1]);
-            *reinterpret_cast<ulonglong2*>(dst + (long long)(r0 + j) * N + i) = o;
-        }
-    }
-}
-
 }  // namespace cuhe_b200

@@ -235,3 +235,14 @@ def test_host_marshalling_equals_oracle_layout(lib):
         assert _raw_np_to_zzx(raw, o.n) == coeffs
     short = _zzx_to_raw_np([5, 6], 2, o.H)                      # a short ZZX is zero-extended
     assert short[0, 0] == 5 and short[1, 0] == 6 and not short[2:].any()
+
+
+def test_lazy_96bit_arithmetic_on_the_host():
+    """cuhe_b200/csrc/l96.cuh + ntt96_core.cuh (the arithmetic inside the NTT kernels) compiled for the CPU with every
+    intermediate an exact 128-bit integer and the 96-bit window enforced: residues, stated magnitudes, the 4/8/16-point
+    blocks against the O(n^2) definition (tests/cpp/l96_host_test.cpp)."""
+    import subprocess
+    exe = os.path.join(ROOT, "tests", "_l96_host_test")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "tests", "cpp", "l96_host_test.cpp")])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "0 failures, 0 window overflows" in r.stdout, r.stdout + r.stderr
