@@ -76,6 +76,10 @@ SYMBOLS = {
     "cuhe_mul_crt_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "cuhe_icrt_batch": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "cuhe_icrt_slice_batch": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "cuhe_comm_unique_id": (_i, [_vp]),
+    "cuhe_ctx_comm_init": (_i, [_vp, _vp]),
+    "cuhe_ctx_comm_attach": (_i, [_vp, _vp]),
+    "cuhe_mul_raw_sharded_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "cuhe_modp_batch": (_i, [_vp, _i, _vp, _vp, _vp, C.c_size_t, _i, _vp]),
     "cuhe_launch_count": (_ll, [_i]),
 }

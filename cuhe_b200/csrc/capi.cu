@@ -24,6 +24,8 @@
 #include "engine.hpp"
 #include "host_math.hpp"
 #include "rns.cuh"
+#include "cyclo.cuh"
+#include "nccl_dl.hpp"
 
 namespace cuhe_b200 {
 
@@ -83,12 +85,20 @@ struct cuhe_ctx {
     // fast reduction modulo Phi_m (needs Phi | x^m - 1): quotient through an Nq-point product,
     // q*Phi through an Nr-point product; tables for the local rows of level 0
     bool fast_reduce = false;
+    // reduction modulo Phi_m by strided differences / prefix sums (cyclo.cuh), when the polynomial modulus is
+    // exactly the m-th cyclotomic polynomial and a residue fits shared memory
+    bool sparse_reduce = false;
+    CycloPlan cyc{};
+    size_t cyc_smem = 0;
     int Nq = 0, Nr = 0, k1 = 0;            // k1 = m - n quotient coefficients
     uint64_t *d_tq = nullptr, *d_tr = nullptr;
     // relinearization keys: [rows(0)][numEvalKey][N]
     uint64_t* d_ek = nullptr;
     // internal streams/events of the pipelined host-buffer entry points
     cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+    // NCCL communicator over the shard_world ranks (cuhe_ctx_comm_init / cuhe_ctx_comm_attach)
+    ncclComm_t comm = nullptr;
+    bool comm_owned = false;
     std::mutex mu;
 
     int L(int lvl) const { return par.numCrtPrimeAt(lvl); }
@@ -268,6 +278,23 @@ static void reduce_fast_impl(cuhe_ctx* c, uint32_t* dst, const uint32_t* hold, i
     CK(cudaGetLastError());
 }
 
+// (f mod Phi_m) for `batch` polynomials when Phi is the m-th cyclotomic polynomial: no transform at all (cyclo.cuh)
+static void reduce_sparse_impl(cuhe_ctx* c, uint32_t* dst, const uint32_t* hold, int lvl, int batch, cudaStream_t st) {
+    const int N = c->par.nttLen, H = c->par.crtLen, n = c->par.modLen, m = c->par.mSize, rows = c->rows(lvl);
+    const int cnt = rows * batch;
+    if (cnt == 0) return;
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !done[dev]) {
+        CK(cudaFuncSetAttribute(cyclo_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        done[dev] = true;
+    }
+    cyclo_reduce_kernel<<<cnt, kCycT, c->cyc_smem, st>>>(dst, hold, c->pv(), rows, n, m, H, N, c->cyc);
+    count_launch();
+    CK(cudaGetLastError());
+}
+
 __global__ void take_low_half_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, int H, int N) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < H) dst[(long long)blockIdx.y * H + i] = src[(long long)blockIdx.y * N + i];
@@ -314,21 +341,22 @@ __global__ void modp_batch_kernel(int op, uint64_t* __restrict__ out, const uint
 
 template <int WMAX>
 static void launch_icrt(uint32_t* dst, const uint32_t* src, cuhe_ctx* c, const IcrtDev& ic, int b, int e, int batch,
-                        int Hs, cudaStream_t st) {
+                        int Hs, cudaStream_t st, int grp_G = 0, int grp_nb = 0) {
     const int cnt = e - b;
     dim3 grid((cnt + 127) / 128, batch);
     if (ic.truncated) {
         icrt_kernel<WMAX><<<grid, 128, 0, st>>>(dst, src, c->d_primes, c->d_mus, ic.M, ic.mi, ic.bi, ic.L, ic.W, ic.Wp, b,
-                                                e, Hs);
+                                                e, Hs, grp_G, grp_nb);
     } else {
         const size_t smem = ((size_t)ic.L * ((ic.Wp + 3) & ~3) + ic.W) * 4;
         icrt_kernel_v2<WMAX><<<grid, 128, smem, st>>>(dst, src, c->d_primes, c->d_mus, ic.M, ic.mi, ic.bi, ic.m_top, ic.L,
-                                                      ic.W, ic.Wp, b, e, Hs);
+                                                      ic.W, ic.Wp, b, e, Hs, grp_G, grp_nb);
     }
     count_launch();
 }
 template <int WMAX>
-static void launch_crt(cuhe_ctx* c, uint32_t* dst, const uint32_t* raw, int rows, int W, int batch, cudaStream_t st) {
+static void launch_crt(cuhe_ctx* c, uint32_t* dst, const uint32_t* raw, PrimeView pv, int rows, int W, int batch,
+                       cudaStream_t st) {
     static bool done[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -339,21 +367,21 @@ static void launch_crt(cuhe_ctx* c, uint32_t* dst, const uint32_t* raw, int rows
     const int H = c->par.crtLen;
     const size_t smem = ((size_t)rows * ((W + 3) & ~3) + (size_t)128 * (W | 1)) * 4;
     dim3 grid((H + 127) / 128, batch);
-    crt_kernel_v2<WMAX><<<grid, 128, smem, st>>>(dst, raw, c->pv(), rows, c->d_pow32, c->pow_stride, W, c->par.modLen, H);
+    crt_kernel_v2<WMAX><<<grid, 128, smem, st>>>(dst, raw, pv, rows, c->d_pow32, c->pow_stride, W, c->par.modLen, H);
     count_launch();
 }
 // ICRT of `batch` polynomials: crt_all u32[batch][L][H] -> raw u32[batch][H][W], coefficients [b,e)
 // Hs = words between consecutive residue rows (and coefficients per RAW polynomial) of the buffers:
 // crtLen for whole polynomials, the slice length for coefficient slices; [b,e) are indices into them
 static void do_icrt_strided(cuhe_ctx* c, uint32_t* raw_out, const uint32_t* crt_all, int lvl, int b, int e, int batch,
-                            int Hs, cudaStream_t st) {
+                            int Hs, cudaStream_t st, int grp_G = 0, int grp_nb = 0) {
     if (b >= e || batch <= 0) return;
     const IcrtDev& ic = c->icrt[lvl];
-    if (ic.W <= 8) launch_icrt<8>(raw_out, crt_all, c, ic, b, e, batch, Hs, st);
-    else if (ic.W <= 20) launch_icrt<20>(raw_out, crt_all, c, ic, b, e, batch, Hs, st);
-    else if (ic.W <= 36) launch_icrt<36>(raw_out, crt_all, c, ic, b, e, batch, Hs, st);
-    else if (ic.W <= 52) launch_icrt<52>(raw_out, crt_all, c, ic, b, e, batch, Hs, st);
-    else if (ic.W <= 104) launch_icrt<104>(raw_out, crt_all, c, ic, b, e, batch, Hs, st);
+    if (ic.W <= 8) launch_icrt<8>(raw_out, crt_all, c, ic, b, e, batch, Hs, st, grp_G, grp_nb);
+    else if (ic.W <= 20) launch_icrt<20>(raw_out, crt_all, c, ic, b, e, batch, Hs, st, grp_G, grp_nb);
+    else if (ic.W <= 36) launch_icrt<36>(raw_out, crt_all, c, ic, b, e, batch, Hs, st, grp_G, grp_nb);
+    else if (ic.W <= 52) launch_icrt<52>(raw_out, crt_all, c, ic, b, e, batch, Hs, st, grp_G, grp_nb);
+    else if (ic.W <= 104) launch_icrt<104>(raw_out, crt_all, c, ic, b, e, batch, Hs, st, grp_G, grp_nb);
     else throw ArgError{"coefficient modulus wider than 104 words"};
     CK(cudaGetLastError());
 }
@@ -362,18 +390,22 @@ static void do_icrt(cuhe_ctx* c, uint32_t* raw_out, const uint32_t* crt_all, int
     if (e > c->par.modLen) e = c->par.modLen;     // the reference writes idx < modLen only
     do_icrt_strided(c, raw_out, crt_all, lvl, b, e, batch, c->par.crtLen, st);
 }
-// CRT of `batch` polynomials: raw u32[batch][H][W] -> dst u32[batch][rows][H]
-static void do_crt(cuhe_ctx* c, uint32_t* dst, const uint32_t* raw, int lvl, int batch, cudaStream_t st) {
-    const int rows = c->rows(lvl), W = c->par.wordsCoeffAt(lvl), H = c->par.crtLen;
+// CRT of `batch` polynomials for the residues of `pv`: raw u32[batch][H][W] -> dst u32[batch][rows][H]
+static void do_crt_view(cuhe_ctx* c, uint32_t* dst, const uint32_t* raw, PrimeView pv, int rows, int lvl, int batch,
+                        cudaStream_t st) {
+    const int W = c->par.wordsCoeffAt(lvl);
     if (rows == 0 || batch <= 0) return;
-    (void)H;
-    if (W <= 8) launch_crt<8>(c, dst, raw, rows, W, batch, st);
-    else if (W <= 20) launch_crt<20>(c, dst, raw, rows, W, batch, st);
-    else if (W <= 36) launch_crt<36>(c, dst, raw, rows, W, batch, st);
-    else if (W <= 52) launch_crt<52>(c, dst, raw, rows, W, batch, st);
-    else if (W <= 104) launch_crt<104>(c, dst, raw, rows, W, batch, st);
+    if (W <= 8) launch_crt<8>(c, dst, raw, pv, rows, W, batch, st);
+    else if (W <= 20) launch_crt<20>(c, dst, raw, pv, rows, W, batch, st);
+    else if (W <= 36) launch_crt<36>(c, dst, raw, pv, rows, W, batch, st);
+    else if (W <= 52) launch_crt<52>(c, dst, raw, pv, rows, W, batch, st);
+    else if (W <= 104) launch_crt<104>(c, dst, raw, pv, rows, W, batch, st);
     else throw ArgError{"coefficient modulus wider than 104 words"};
     CK(cudaGetLastError());
+}
+// ... for the residues this context owns
+static void do_crt(cuhe_ctx* c, uint32_t* dst, const uint32_t* raw, int lvl, int batch, cudaStream_t st) {
+    do_crt_view(c, dst, raw, c->pv(), c->rows(lvl), lvl, batch, st);
 }
 
 }  // namespace cuhe_b200
@@ -515,6 +547,9 @@ int cuhe_ctx_create(cuhe_ctx** out, const cuhe_params* p, int device, int shard_
             hm::IcrtConst ic = hm::gen_icrt(c->par, c->primes, c->moduli, lvl);
             IcrtDev d;
             d.L = ic.L; d.W = ic.W; d.Wp = ic.Wp; d.truncated = ic.truncated;
+            // CUHE_B200_LITERAL_ICRT=1 (read at context creation): always run the literal add / compare / subtract
+            // kernel, the one a byte-truncated M_l needs -- lets the parity suite reach it with ordinary parameters
+            { const char* sp = getenv("CUHE_B200_LITERAL_ICRT"); if (sp && sp[0] == '1') d.truncated = true; }
             for (int k = std::max(0, ic.W - 3); k < ic.W; k++)      // M / 2^(32(W-2)) from its top three words
                 d.m_top += (double)ic.M[k] * __builtin_ldexp(1.0, 32 * (k - (ic.W - 2)));
             d.M = upload(ic.M); d.mi = upload(ic.mi); d.bi = upload(ic.bi);
@@ -537,6 +572,7 @@ int cuhe_ctx_destroy(cuhe_ctx* c) {
         cudaFree(c->d_u_ntt); cudaFree(c->d_m_ntt); cudaFree(c->d_m_crt); cudaFree(c->d_ek);
         cudaFree(c->d_tq); cudaFree(c->d_tr);
         if (c->s_h2d) { cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_comp); cudaStreamDestroy(c->s_d2h); }
+        if (c->comm && c->comm_owned) { if (NcclApi* api = nccl_api(nullptr)) api->CommDestroy(c->comm); }
         if (c->pool) cudaMemPoolDestroy(c->pool);
         delete c;
     });
@@ -637,6 +673,25 @@ int cuhe_ctx_set_poly_modulus_host(cuhe_ctx* c, const int64_t* coeffs, int ncoef
             }
             get_plan(c, Nq); get_plan(c, Nr);
             c->fast_reduce = true;
+        }
+        // ---- sparse reduction (Phi exactly the m-th cyclotomic polynomial; CUHE_B200_REDUCE=ntt|barrett opts out) ----
+        c->sparse_reduce = false;
+        {
+            const char* mode = getenv("CUHE_B200_REDUCE");
+            const bool want = !(force && force[0] == '1') && !(mode && (mode[0] == 'n' || mode[0] == 'b'));
+            if (mode && mode[0] == 'b') c->fast_reduce = false;
+            hm::CycloFactors cf = hm::cyclo_factors(phi, m);
+            std::vector<int> B;
+            for (int d : cf.plus) if (d != m) B.push_back(d);
+            const size_t smem = ((size_t)((n + 3) & ~3) + ((k1 + 3) & ~3) + kCycT) * 4;
+            if (want && cf.ok && k1 >= 1 && n <= kCycMaxK * kCycT && m <= N && 2 * n - 2 < 2 * m && smem <= 227 * 1024 &&
+                (int)cf.minus.size() <= kCycMaxFactors && (int)B.size() <= kCycMaxFactors) {
+                c->cyc.nD = (int)cf.minus.size(); c->cyc.nB = (int)B.size();
+                for (int i = 0; i < c->cyc.nD; i++) c->cyc.D[i] = cf.minus[i];
+                for (int i = 0; i < c->cyc.nB; i++) c->cyc.B[i] = B[i];
+                c->cyc_smem = smem;
+                c->sparse_reduce = true;
+            }
         }
         c->have_polymod = true;
     });
@@ -743,7 +798,8 @@ static void intt_mod_impl(cuhe_ctx* c, uint32_t* dst, const uint64_t* x, const u
     if (!c->have_polymod) throw StateError{"Barrett reduction needs cuhe_ctx_set_poly_modulus_host first"};
     Tmp hold(c, (size_t)rows * batch * N * 4, st);
     inv_ntt_modp(c, N, hold.as<uint32_t>(), x, y, rows * batch, rows, st);
-    if (c->fast_reduce) reduce_fast_impl(c, dst, hold.as<uint32_t>(), lvl, batch, st);
+    if (c->sparse_reduce) reduce_sparse_impl(c, dst, hold.as<uint32_t>(), lvl, batch, st);
+    else if (c->fast_reduce) reduce_fast_impl(c, dst, hold.as<uint32_t>(), lvl, batch, st);
     else barrett_impl(c, dst, hold.as<uint32_t>(), lvl, batch, st);
 }
 // raw a,b u32[batch][H][W] (device) -> product residues u32[batch][rows][H]
@@ -1038,5 +1094,119 @@ int cuhe_mul_raw_host_batch(cuhe_ctx* c, uint32_t* out_h, const uint32_t* a_h, c
         cudaEventDestroy(ready);
     });
 }
+
+// ---- residue-sharded products with the exchange inside the library --------------------------------------
+#define NK(call)                                                                                   \
+    do {                                                                                           \
+        ncclResult_t _r = (call);                                                                  \
+        if (_r != ncclSuccess) throw StateError{std::string("NCCL: ") + api->GetErrorString(_r) + " in " #call}; \
+    } while (0)
+
+int cuhe_comm_unique_id(void* id_out) {
+    return guarded([&] {
+        REQUIRE(id_out != nullptr, "null argument");
+        std::string why;
+        NcclApi* api = nccl_api(&why);
+        if (!api) throw StateError{why};
+        ncclUniqueId id;
+        NK(api->GetUniqueId(&id));
+        memcpy(id_out, &id, sizeof id);
+    });
+}
+int cuhe_ctx_comm_init(cuhe_ctx* c, const void* id_bytes) {
+    return guarded([&] {
+        REQUIRE(c && id_bytes, "null argument");
+        REQUIRE(c->comm == nullptr, "the context already has a communicator");
+        std::string why;
+        NcclApi* api = nccl_api(&why);
+        if (!api) throw StateError{why};
+        DeviceGuard dg(c->device);
+        ncclUniqueId id;
+        memcpy(&id, id_bytes, sizeof id);
+        NK(api->CommInitRank(&c->comm, c->world, id, c->rank));
+        c->comm_owned = true;
+    });
+}
+int cuhe_ctx_comm_attach(cuhe_ctx* c, void* nccl_comm) {
+    return guarded([&] {
+        REQUIRE(c && nccl_comm, "null argument");
+        REQUIRE(c->comm == nullptr, "the context already has a communicator");
+        std::string why;
+        NcclApi* api = nccl_api(&why);
+        if (!api) throw StateError{why};
+        int n = 0, r = -1;
+        NK(api->CommCount((ncclComm_t)nccl_comm, &n));
+        NK(api->CommUserRank((ncclComm_t)nccl_comm, &r));
+        REQUIRE(n == c->world && r == c->rank, "communicator size / rank differ from the context's shard");
+        c->comm = (ncclComm_t)nccl_comm;
+        c->comm_owned = false;
+    });
+}
+
+// Every rank multiplies its OWN `nb` ciphertext pairs (device RAW in, device RAW out) with the residue axis of all
+// nb*G products spread over the G ranks:
+//   1. CRT of the own operands for every rank's primes, grouped by destination rank        (local)
+//   2. all-to-all: rank j receives the rows of ITS primes of all nb*G products              (NVLink, 2*nb*L*H*4*(G-1)/G bytes out)
+//   3. forward transforms, pointwise product, inverse transforms, reduction mod Phi_m       (local, rows(lvl) x nb*G)
+//   4. all-to-all back: the owner of a product receives all its residue rows                (nb*L*H*4*(G-1)/G bytes out)
+//   5. ICRT of the own products straight from the grouped receive buffer                    (local; cuhe/CuHE.cu:366-382)
+// No rank ever holds data of products it does not own except the residue rows it transforms.
+int cuhe_mul_raw_sharded_batch(cuhe_ctx* c, uint32_t* raw_out, const uint32_t* a_raw, const uint32_t* b_raw, int lvl, int nb,
+                               cuhe_stream stream) {
+    return guarded([&] {
+        check_lvl(c, lvl); REQUIRE(raw_out && a_raw && b_raw, "null pointer");
+        REQUIRE(nb >= 1, "bad batch");
+        DeviceGuard dg(c->device);
+        cudaStream_t st = (cudaStream_t)stream;
+        const int G = c->world, me = c->rank, L = c->L(lvl), H = c->par.crtLen, N = c->par.nttLen, n = c->par.modLen;
+        if (G == 1) {
+            Tmp cc(c, (size_t)nb * L * H * 4, st);
+            mul_crt_batch_impl(c, cc.as<uint32_t>(), a_raw, b_raw, lvl, nb, st);
+            do_icrt(c, raw_out, cc.as<uint32_t>(), lvl, 0, n, nb, st);
+            return;
+        }
+        if (!c->comm) throw StateError{"cuhe_ctx_comm_init / cuhe_ctx_comm_attach has not been called"};
+        std::string why;
+        NcclApi* api = nccl_api(&why);
+        if (!api) throw StateError{why};
+        const long long B = (long long)nb * G;
+        auto rows_of = [&](int j) { return j < L ? (L - j + G - 1) / G : 0; };
+        auto pre = [&](int j) { const int qq = L / G, rr = L % G; return j * qq + (j < rr ? j : rr); };
+        const int rows_me = rows_of(me);
+        REQUIRE(2 * B * rows_me <= 65535, "batch too large");
+        const size_t seg_me = (size_t)nb * rows_me * H;                       // words per (operand, peer) on the receive side
+        Tmp send(c, (size_t)2 * nb * L * H * 4, st), ca(c, std::max<size_t>(1, (size_t)2 * B * rows_me * H * 4), st);
+        uint32_t* snd[2] = {send.as<uint32_t>(), send.as<uint32_t>() + (size_t)nb * L * H};
+        uint32_t* rcv[2] = {ca.as<uint32_t>(), ca.as<uint32_t>() + (size_t)B * rows_me * H};
+        const uint32_t* raws[2] = {a_raw, b_raw};
+        for (int op = 0; op < 2; op++)
+            for (int j = 0; j < G; j++)
+                do_crt_view(c, snd[op] + (size_t)nb * pre(j) * H, raws[op], PrimeView{c->d_primes, c->d_mus, j, G}, rows_of(j),
+                            lvl, nb, st);
+        NK(api->GroupStart());
+        for (int op = 0; op < 2; op++)
+            for (int j = 0; j < G; j++) {
+                if (rows_of(j) > 0) NK(api->Send(snd[op] + (size_t)nb * pre(j) * H, (size_t)nb * rows_of(j) * H * 4, ncclUint8, j, c->comm, st));
+                if (rows_me > 0) NK(api->Recv(rcv[op] + (size_t)j * seg_me, seg_me * 4, ncclUint8, j, c->comm, st));
+            }
+        NK(api->GroupEnd());
+        const long long cnt = B * rows_me;
+        Tmp prod(c, std::max<size_t>(1, (size_t)cnt * H * 4), st), full(c, (size_t)nb * L * H * 4, st);
+        if (cnt > 0) {
+            if (!c->have_polymod) throw StateError{"Barrett reduction needs cuhe_ctx_set_poly_modulus_host first"};
+            Tmp nab(c, (size_t)2 * cnt * N * 8, st);
+            fwd_ntt(c, N, nab.as<uint64_t>(), ca.as<uint32_t>(), H, (int)(2 * cnt), nullptr, 1, st);
+            intt_mod_impl(c, prod.as<uint32_t>(), nab.as<uint64_t>(), nab.as<uint64_t>() + (size_t)cnt * N, lvl, (int)B, st);
+        }
+        NK(api->GroupStart());
+        for (int j = 0; j < G; j++) {
+            if (rows_me > 0) NK(api->Send(prod.as<uint32_t>() + (size_t)j * seg_me, seg_me * 4, ncclUint8, j, c->comm, st));
+            if (rows_of(j) > 0) NK(api->Recv(full.as<uint32_t>() + (size_t)nb * pre(j) * H, (size_t)nb * rows_of(j) * H * 4, ncclUint8, j, c->comm, st));
+        }
+        NK(api->GroupEnd());
+        do_icrt_strided(c, raw_out, full.as<uint32_t>(), lvl, 0, n, nb, H, st, G, nb);
+    });
+}
+#undef NK
 
 }  // extern "C"

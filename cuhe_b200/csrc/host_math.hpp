@@ -308,5 +308,49 @@ inline bool divides_xm_minus_1(const std::vector<int64_t>& phi, int m) {
     return true;
 }
 
+
+// ---- Phi_m as a quotient of binomials ---------------------------------------------------------------
+// Phi_m(x) = prod_{d | m} (x^d - 1)^mu(m/d).  plus = {d : mu(m/d) = +1} (contains m), minus = {d : mu(m/d) = -1}.
+// Used by the sparse reduction modulo Phi_m (cyclo.cuh): multiplying / dividing a power series by (1 - x^d) is a
+// strided difference / prefix sum, so no transform is needed to reduce modulo a cyclotomic polynomial.
+struct CycloFactors {
+    std::vector<int> plus, minus;
+    bool ok = false;
+};
+inline int mobius(int v) {
+    int mu = 1;
+    for (int q = 2; (long long)q * q <= v; q++) {
+        if (v % q == 0) {
+            v /= q;
+            if (v % q == 0) return 0;
+            mu = -mu;
+        }
+    }
+    if (v > 1) mu = -mu;
+    return mu;
+}
+// returns ok = true iff phi is exactly the m-th cyclotomic polynomial (checked by rebuilding it from the binomials)
+inline CycloFactors cyclo_factors(const std::vector<int64_t>& phi, int m) {
+    CycloFactors f;
+    const int n = (int)phi.size() - 1;
+    if (m < 2 || n < 1 || n >= m) return f;
+    for (int d = 1; d <= m; d++) {
+        if (m % d) continue;
+        const int mu = mobius(m / d);
+        if (mu > 0) f.plus.push_back(d);
+        else if (mu < 0) f.minus.push_back(d);
+    }
+    // Phi as a power series mod x^(n+1): prod_plus (1 - x^d) / prod_minus (1 - x^d)   (|plus| = |minus| for m > 1,
+    // so the sign of (x^d - 1) vs (1 - x^d) cancels); compare with phi
+    if (f.plus.size() != f.minus.size()) return f;
+    std::vector<int64_t> a(n + 1, 0);
+    a[0] = 1;
+    for (int d : f.plus) for (int i = n; i >= d; i--) a[i] -= a[i - d];
+    for (int d : f.minus) for (int i = d; i <= n; i++) a[i] += a[i - d];
+    for (int i = 0; i <= n; i++) if (a[i] != phi[i]) return f;
+    f.ok = true;
+    return f;
+}
+
 }  // namespace hm
 }  // namespace cuhe_b200

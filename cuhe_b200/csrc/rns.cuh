@@ -19,6 +19,19 @@ namespace cuhe_b200 {
 
 __device__ __forceinline__ int prime_index(const PrimeView& v, int row) { return v.base + v.step * row; }
 
+
+// Where the residue row of prime l of polynomial `batch` starts in an ICRT source buffer.
+//   G <= 1: [batch][L][H] in prime order (the reference layout, cuhe/Base.cu:880-924).
+//   G  > 1: the layout an all-to-all from G residue-sharded ranks leaves behind (cuhe_mul_raw_sharded_batch):
+//           G groups, group j = [nb][rows_j][H] holding primes j, j+G, j+2G, ... of the nb polynomials, where
+//           rows_j = ceil((L - j) / G); groups are packed back to back.
+__device__ __forceinline__ long long icrt_src_row(int l, int batch, int L, int H, int G, int nb) {
+    if (G <= 1) return ((long long)batch * L + l) * H;
+    const int j = l % G, i = l / G, qq = L / G, rr = L % G;
+    const int rows_j = qq + (j < rr ? 1 : 0), pre = j * qq + (j < rr ? j : rr);
+    return ((long long)nb * pre + (long long)batch * rows_j + i) * H;
+}
+
 // ---------------------------------------------------------------------------
 // ICRT: u32[L][H] -> raw u32[H][W]                          (cuhe/Base.cu:845-924)
 // coeff = sum_l ((c_l * b_l mod p_l) * M_l), one conditional subtraction of M
@@ -30,10 +43,10 @@ template <int WMAX>
 __global__ void __launch_bounds__(128)
 icrt_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, const uint32_t* __restrict__ primes,
             const uint64_t* __restrict__ mus, const uint32_t* __restrict__ M, const uint32_t* __restrict__ mi,
-            const uint32_t* __restrict__ bi, int L, int W, int Wp, int i_begin, int i_end, int H) {
+            const uint32_t* __restrict__ bi, int L, int W, int Wp, int i_begin, int i_end, int H, int grp_G, int grp_nb) {
     const int idx = i_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= i_end) return;
-    src += (long long)blockIdx.y * L * H;           // batch
+    const int bat = blockIdx.y;                      // batch
     dst += (long long)blockIdx.y * H * W;
     uint32_t sum[WMAX + 1];
 #pragma unroll
@@ -41,7 +54,7 @@ icrt_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, const 
     for (int l = 0; l < L; l++) {
         const uint32_t p = primes[l];
         const uint64_t mu = mus[l];
-        uint64_t tar = mod_u64_u32(src[(long long)l * H + idx], p, mu);
+        uint64_t tar = mod_u64_u32(src[icrt_src_row(l, bat, L, H, grp_G, grp_nb) + idx], p, mu);
         const uint32_t tt = mod_u64_u32(tar * bi[l], p, mu);
         const uint32_t* m = mi + (long long)l * Wp;
         uint64_t carry = 0;
@@ -92,7 +105,7 @@ icrt_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, const 
 template <int WMAX>
 __global__ void __launch_bounds__(128)
 crt_kernel_v2(uint32_t* __restrict__ dst, const uint32_t* __restrict__ raw, PrimeView pv, int rows,
-              const uint32_t* __restrict__ pow32, int pow_stride, int W, int n, int H) {
+              const uint32_t* __restrict__ pow32, int pow_stride, int W, int n, int H) {   // dst: [batch][rows][H]
     extern __shared__ uint32_t sh[];          // [rows][W4] powers (rows padded to 4 words), then [128][W|1] staging
     const int W4 = (W + 3) & ~3;
     uint32_t* spw = sh;
@@ -122,23 +135,40 @@ crt_kernel_v2(uint32_t* __restrict__ dst, const uint32_t* __restrict__ raw, Prim
     for (int r = 0; r < rows; r++) {
         const int l = prime_index(pv, r);
         const uint32_t* pw = spw + r * W4;
-        uint64_t acc = 0, acc_hi = 0;         // p < 2^26: 16 products stay below 2^62
-#pragma unroll
-        for (int k = 0; k < WMAX; k += 4) {   // one 128-bit broadcast load feeds four multiply-adds
-            if (k < W) {
-                const uint4 q = *reinterpret_cast<const uint4*>(pw + k);     // words >= W are zero (c[] too)
-                acc += (uint64_t)c[k] * q.x;
-                if (k + 1 < WMAX) acc += (uint64_t)c[k + 1 < WMAX ? k + 1 : 0] * q.y;
-                if (k + 2 < WMAX) acc += (uint64_t)c[k + 2 < WMAX ? k + 2 : 0] * q.z;
-                if (k + 3 < WMAX) acc += (uint64_t)c[k + 3 < WMAX ? k + 3 : 0] * q.w;
-                if ((k & 15) == 12) { acc_hi += acc >> 32; acc &= 0xFFFFFFFFull; }
-            }
-        }
         const uint32_t p = pv.p[l];
         const uint64_t mu = pv.mu[l];
-        const uint64_t t = mod_u64_u32(acc_hi, p, mu);
-        const uint32_t two32 = W > 1 ? pw[1] : (uint32_t)((1ull << 32) % p);
-        dst[(long long)r * H + i] = mod_u64_u32(t * two32 + mod_u64_u32(acc, p, mu), p, mu);
+        if constexpr (WMAX <= 36) {
+            // p < 2^26: every product is below 2^58, so up to 63 of them fit one 64-bit sum -- two independent
+            // accumulators (even / odd words) and ONE reduction per residue (round 1 reduced three times)
+            uint64_t a0 = 0, a1 = 0;
+#pragma unroll
+            for (int k = 0; k < WMAX; k += 4) {   // one 128-bit broadcast load feeds four multiply-adds
+                if (k < W) {
+                    const uint4 q = *reinterpret_cast<const uint4*>(pw + k);     // words >= W are zero (c[] too)
+                    a0 += (uint64_t)c[k] * q.x;
+                    if (k + 1 < WMAX) a1 += (uint64_t)c[k + 1 < WMAX ? k + 1 : 0] * q.y;
+                    if (k + 2 < WMAX) a0 += (uint64_t)c[k + 2 < WMAX ? k + 2 : 0] * q.z;
+                    if (k + 3 < WMAX) a1 += (uint64_t)c[k + 3 < WMAX ? k + 3 : 0] * q.w;
+                }
+            }
+            dst[(long long)r * H + i] = mod_u64_u32(a0 + a1, p, mu);
+        } else {
+            uint64_t acc = 0, acc_hi = 0;         // 16 products stay below 2^62
+#pragma unroll
+            for (int k = 0; k < WMAX; k += 4) {
+                if (k < W) {
+                    const uint4 q = *reinterpret_cast<const uint4*>(pw + k);
+                    acc += (uint64_t)c[k] * q.x;
+                    if (k + 1 < WMAX) acc += (uint64_t)c[k + 1 < WMAX ? k + 1 : 0] * q.y;
+                    if (k + 2 < WMAX) acc += (uint64_t)c[k + 2 < WMAX ? k + 2 : 0] * q.z;
+                    if (k + 3 < WMAX) acc += (uint64_t)c[k + 3 < WMAX ? k + 3 : 0] * q.w;
+                    if ((k & 15) == 12) { acc_hi += acc >> 32; acc &= 0xFFFFFFFFull; }
+                }
+            }
+            const uint64_t t = mod_u64_u32(acc_hi, p, mu);
+            const uint32_t two32 = W > 1 ? pw[1] : (uint32_t)((1ull << 32) % p);
+            dst[(long long)r * H + i] = mod_u64_u32(t * two32 + mod_u64_u32(acc, p, mu), p, mu);
+        }
     }
 }
 
@@ -155,7 +185,8 @@ template <int WMAX>
 __global__ void __launch_bounds__(128)
 icrt_kernel_v2(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, const uint32_t* __restrict__ primes,
                const uint64_t* __restrict__ mus, const uint32_t* __restrict__ M, const uint32_t* __restrict__ mi,
-               const uint32_t* __restrict__ bi, double m_top, int L, int W, int Wp, int i_begin, int i_end, int H) {
+               const uint32_t* __restrict__ bi, double m_top, int L, int W, int Wp, int i_begin, int i_end, int H,
+               int grp_G, int grp_nb) {
     extern __shared__ uint32_t sh[];          // [L][Wp4] M_l (rows zero-padded to 4 words), [W] M
     const int Wp4 = (Wp + 3) & ~3;
     uint32_t* smi = sh;
@@ -168,28 +199,76 @@ icrt_kernel_v2(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, con
     __syncthreads();
     const int idx = i_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= i_end) return;
-    src += (long long)blockIdx.y * L * H;
+    const int bat = blockIdx.y;
     dst += (long long)blockIdx.y * H * W;
     uint32_t sum[WMAX + 4];
+    if constexpr (WMAX <= 52) {
+        // Row multiply-accumulate as two carry chains that ptxas fuses into IMAD.WIDE.U32.X (one FMA-pipe
+        // instruction per word): E takes the products of the even words of M_l, O those of the odd words
+        // (O[j] has weight 2^(32(j+1))); separate arrays keep both chains on aligned register pairs.
+        // Round 1 spent ~4 ALU-pipe instructions per word on 64-bit add/shift carries.
+        constexpr int WE = (WMAX + 3) & ~3;
+        uint32_t E[WE + 2], O[WE + 2];
 #pragma unroll
-    for (int k = 0; k < WMAX + 4; k++) sum[k] = 0;
-    for (int l = 0; l < L; l++) {
-        const uint32_t p = primes[l];
-        const uint64_t mu = mus[l];
-        const uint64_t tar = mod_u64_u32(src[(long long)l * H + idx], p, mu);
-        const uint32_t tt = mod_u64_u32(tar * bi[l], p, mu);
-        const uint32_t* m = smi + l * Wp4;
-        uint64_t carry = 0;
+        for (int k = 0; k < WE + 2; k++) E[k] = O[k] = 0;
+        for (int l = 0; l < L; l++) {
+            // (c mod p) * b mod p == (c * b) mod p: one reduction (c < 2^32, b < 2^26)
+            const uint32_t tt = mod_u64_u32((uint64_t)src[icrt_src_row(l, bat, L, H, grp_G, grp_nb) + idx] * bi[l], primes[l], mus[l]);
+            const uint32_t* m = smi + l * Wp4;
+            uint32_t mm[WE];
 #pragma unroll
-        for (int k = 0; k < WMAX + 4; k += 4) {      // one 128-bit broadcast load per four multiply-adds
-            if (k <= W) {
+            for (int k = 0; k < WE; k += 4) {
                 uint4 q = make_uint4(0u, 0u, 0u, 0u);
                 if (k < Wp4) q = *reinterpret_cast<const uint4*>(m + k);
-                uint64_t t;
-                t = (uint64_t)sum[k] + carry + (uint64_t)tt * q.x;     sum[k] = (uint32_t)t;     carry = t >> 32;
-                t = (uint64_t)sum[k + 1] + carry + (uint64_t)tt * q.y; sum[k + 1] = (uint32_t)t; carry = t >> 32;
-                t = (uint64_t)sum[k + 2] + carry + (uint64_t)tt * q.z; sum[k + 2] = (uint32_t)t; carry = t >> 32;
-                t = (uint64_t)sum[k + 3] + carry + (uint64_t)tt * q.w; sum[k + 3] = (uint32_t)t; carry = t >> 32;
+                mm[k] = q.x; mm[k + 1] = q.y; mm[k + 2] = q.z; mm[k + 3] = q.w;
+            }
+            asm volatile("mad.lo.cc.u32 %0, %1, %2, %0;" : "+r"(E[0]) : "r"(tt), "r"(mm[0]));
+            asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(E[1]) : "r"(tt), "r"(mm[0]));
+#pragma unroll
+            for (int k = 2; k < WE; k += 2) {
+                asm volatile("madc.lo.cc.u32 %0, %1, %2, %0;" : "+r"(E[k]) : "r"(tt), "r"(mm[k]));
+                asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(E[k + 1]) : "r"(tt), "r"(mm[k]));
+            }
+            asm volatile("addc.u32 %0, %0, 0;" : "+r"(E[WE]));
+            asm volatile("mad.lo.cc.u32 %0, %1, %2, %0;" : "+r"(O[0]) : "r"(tt), "r"(mm[1]));
+            asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(O[1]) : "r"(tt), "r"(mm[1]));
+#pragma unroll
+            for (int k = 3; k < WE; k += 2) {
+                asm volatile("madc.lo.cc.u32 %0, %1, %2, %0;" : "+r"(O[k - 1]) : "r"(tt), "r"(mm[k]));
+                asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(O[k]) : "r"(tt), "r"(mm[k]));
+            }
+            asm volatile("addc.u32 %0, %0, 0;" : "+r"(O[WE]));
+        }
+        // sum = E + (O << 32)
+        uint64_t carry = 0;
+#pragma unroll
+        for (int k = 0; k < WMAX + 4; k++) {
+            const uint64_t t = (uint64_t)(k < WE + 2 ? E[k < WE + 2 ? k : 0] : 0u) +
+                               (uint64_t)((k >= 1 && k - 1 < WE + 2) ? O[(k >= 1 && k - 1 < WE + 2) ? k - 1 : 0] : 0u) + carry;
+            sum[k] = (uint32_t)t;
+            carry = t >> 32;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < WMAX + 4; k++) sum[k] = 0;
+        for (int l = 0; l < L; l++) {
+            const uint32_t p = primes[l];
+            const uint64_t mu = mus[l];
+            const uint64_t tar = mod_u64_u32(src[icrt_src_row(l, bat, L, H, grp_G, grp_nb) + idx], p, mu);
+            const uint32_t tt = mod_u64_u32(tar * bi[l], p, mu);
+            const uint32_t* m = smi + l * Wp4;
+            uint64_t carry = 0;
+#pragma unroll
+            for (int k = 0; k < WMAX + 4; k += 4) {      // one 128-bit broadcast load per four multiply-adds
+                if (k <= W) {
+                    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+                    if (k < Wp4) q = *reinterpret_cast<const uint4*>(m + k);
+                    uint64_t t;
+                    t = (uint64_t)sum[k] + carry + (uint64_t)tt * q.x;     sum[k] = (uint32_t)t;     carry = t >> 32;
+                    t = (uint64_t)sum[k + 1] + carry + (uint64_t)tt * q.y; sum[k + 1] = (uint32_t)t; carry = t >> 32;
+                    t = (uint64_t)sum[k + 2] + carry + (uint64_t)tt * q.z; sum[k + 2] = (uint32_t)t; carry = t >> 32;
+                    t = (uint64_t)sum[k + 3] + carry + (uint64_t)tt * q.w; sum[k + 3] = (uint32_t)t; carry = t >> 32;
+                }
             }
         }
     }

@@ -195,6 +195,27 @@ int cuhe_icrt_batch(cuhe_ctx* ctx, uint32_t* raw_out, const uint32_t* crt_all, i
 int cuhe_icrt_slice_batch(cuhe_ctx* ctx, uint32_t* raw_slice_out, const uint32_t* crt_slice, int lvl, int coef_offset,
                           int slice_len, int batch, cuhe_stream stream);
 
+/* ---- residue-sharded products over the GPUs of one box, exchange inside the library.
+ * No reference counterpart: the reference keeps whole ciphertexts per device (one OpenMP thread per GPU,
+ * examples/Prince/Prince.cu:194-201; cudaMemcpyPeer in moveTo/copyTo, cuhe/CuHE.cu:217-256).  Here a context
+ * created with (shard_rank, shard_world) owns the primes shard_rank, shard_rank + shard_world, ...; the residue
+ * rows of a product travel between the ranks with NCCL send/recv over NVLink at the two points where the
+ * algorithm needs every residue of a coefficient or every coefficient of a residue: after CRT and before ICRT
+ * (the recombine step of c2r, cuhe/CuHE.cu:366-382).  libnccl.so.2 is bound at run time (dlopen), so single-GPU
+ * users do not need it.
+ *   cuhe_comm_unique_id      rank 0: 128 bytes to hand to every rank by any transport (ncclGetUniqueId)
+ *   cuhe_ctx_comm_init       collective over the shard_world ranks of the context (ncclCommInitRank)
+ *   cuhe_ctx_comm_attach     or: adopt an existing ncclComm_t of the same size and rank (not destroyed with the context)
+ *   cuhe_mul_raw_sharded_batch   collective: every rank passes its OWN `batch` ciphertext pairs (device RAW
+ *       u32[batch][rawLen][W]) and gets the complete RAW products of those pairs back; all ranks pass the same
+ *       batch and level.  With shard_world == 1 it is cuhe_mul_crt_batch + cuhe_icrt_batch. */
+#define CUHE_COMM_ID_BYTES 128
+int cuhe_comm_unique_id(void* id_out_128_bytes);
+int cuhe_ctx_comm_init(cuhe_ctx* ctx, const void* id_128_bytes);
+int cuhe_ctx_comm_attach(cuhe_ctx* ctx, void* nccl_comm);
+int cuhe_mul_raw_sharded_batch(cuhe_ctx* ctx, uint32_t* raw_out, const uint32_t* a_raw, const uint32_t* b_raw, int lvl,
+                               int batch, cuhe_stream stream);
+
 /* ---- device mod-P primitives on arrays: what tests/test_ModP.cu:57-137 drives
  *      (_add/_sub/_mul/_ls_modP of cuhe/ModP.h:68-289).  op: 0 add, 1 sub, 2 mul,
  *      3 shift-left by `shift` bits (0 <= shift < 192), 4 the relinearization

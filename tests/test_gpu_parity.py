@@ -216,6 +216,33 @@ def test_crt_ntt_intt_icrt(which, request):
         assert o.from_raw(got_raw) == coeffs
 
 
+@pytest.mark.parametrize("ps", [SIMPLE_DHS, MID32K, MID64K])
+def test_literal_icrt_kernel(lib, monkeypatch, ps):
+    """The literal ICRT kernel (the reference's add one term / compare / subtract M loop, cuhe/Base.cu:880-924; the
+    path a byte-truncated M_l takes, cuhe/Operations.cu:127-128) forced through CUHE_B200_LITERAL_ICRT=1, whole
+    polynomials and coefficient slices, both levels."""
+    monkeypatch.setenv("CUHE_B200_LITERAL_ICRT", "1")
+    e = Eng(lib, ps)
+    try:
+        o = e.orc
+        for lvl in (0, 1):
+            L, W, H = o.L(lvl), o.W(lvl), o.H
+            coeffs, raw = rand_poly_raw(o, lvl, 300 + lvl)
+            want_crt = o.crt(raw, lvl)
+            d_raw2 = e.empty((H, W), np.uint32)
+            e.call("cuhe_icrt", p(d_raw2), p(e.up(want_crt)), lvl, 0, H, e.st())
+            got = Eng.dn(d_raw2, np.uint32)
+            assert np.array_equal(got, o.icrt(want_crt, lvl))
+            assert o.from_raw(got) == coeffs
+            # a coefficient range only
+            d_part = e.empty((H, W), np.uint32)
+            e.call("cuhe_icrt", p(d_part), p(e.up(want_crt)), lvl, 100, 1000, e.st())
+            part = Eng.dn(d_part, np.uint32)
+            assert np.array_equal(part[100:1000], got[100:1000]) and not part[:100].any() and not part[1000:].any()
+    finally:
+        e.close()
+
+
 @pytest.mark.parametrize("which", ["eng16", "eng32", "eng64"])
 def test_mul_barrett(which, request):
     """ctxt x ctxt: NTT-domain product -> inttMod (INTT + polynomial Barrett)."""
@@ -250,6 +277,37 @@ def test_mul_barrett(which, request):
         got = Eng.dn(d_out, np.uint32)
         for l in range(L):
             assert np.array_equal(got[l, :o.n], np.array([v % o.primes[l] for v in ex], dtype=np.uint32))
+
+
+@pytest.mark.parametrize("mode", ["sparse", "ntt", "barrett"])
+@pytest.mark.parametrize("ps", [SIMPLE_DHS, MID32K, MID64K, (3, 2, 16, 40, 20, 1155)])
+def test_three_reductions_modulo_phi_agree(lib, monkeypatch, ps, mode):
+    """inttMod through each of the three exact reductions modulo Phi_m -- strided differences / prefix sums over the
+    binomial factors of Phi_m (default), the fold + inverse-series products of round 1 (CUHE_B200_REDUCE=ntt) and the
+    reference's Barrett step order (CUHE_B200_REDUCE=barrett, cuhe/Operations.cu:460-501) -- against the oracle, at a
+    prime m (8191), two three-prime m (21845, 32767) and m = 1155 = 3*5*7*11 (16 binomials, quotient longer than the
+    remainder), at level 0 and level 1."""
+    monkeypatch.setenv("CUHE_B200_REDUCE", mode)
+    e = Eng(lib, ps)
+    try:
+        o = e.orc
+        for lvl in (0, 1):
+            L, H, N = o.L(lvl), o.H, o.N
+            _, ra = rand_poly_raw(o, lvl, 61 + lvl)
+            _, rb = rand_poly_raw(o, lvl, 71 + lvl)
+            want = o.mul_raw_to_crt(ra, rb, lvl)
+            na, nb = o.ntt(o.crt(ra, lvl)), o.ntt(o.crt(rb, lvl))
+            d_out = e.empty((L, H), np.uint32)
+            e.call("cuhe_ntt_mul_intt_mod", p(d_out), p(e.up(na)), p(e.up(nb)), lvl, e.st())
+            assert np.array_equal(Eng.dn(d_out, np.uint32), want)
+            # worst-case magnitudes: every coefficient p-1
+            top = np.stack([np.full(H, pr - 1, dtype=np.uint32) for pr in o.primes[:L]])
+            top[:, o.n:] = 0
+            nt = o.ntt(top)
+            e.call("cuhe_ntt_mul_intt_mod", p(d_out), p(e.up(nt)), p(e.up(nt)), lvl, e.st())
+            assert np.array_equal(Eng.dn(d_out, np.uint32), o.intt_mod(__import__("oracle.oracle", fromlist=["x"]).ntt_mul(nt, nt)))
+    finally:
+        e.close()
 
 
 def test_pointwise_and_crt_adds(eng16):
