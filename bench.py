@@ -7,12 +7,12 @@ configs[1]: ring degree 2^15 -> NTT length 65536, 24 CRT primes), with the
   python bench.py --impl reference --gpus N --steps K ...  # CPU arm (oracle port)
   torchrun --nproc-per-node N bench.py --gpus N ...        # residues sharded over N GPUs
 
-A "step" = one batch of B = batch x N_gpus independent ciphertext products, RAW operands
-resident in HBM -> RAW product in HBM (crt x2, forward NTT x2L, fused pointwise
-mul + inverse NTT, polynomial Barrett (2 more forward + 2 more inverse NTTs per
-residue), ICRT).  With N > 1 the CRT-residue axis is sharded (rank r owns primes
-r, r+N, ...), ICRT is split by coefficient range: an NCCL all-to-all hands rank j the
-coefficient slice j of every residue, and the RAW slices are all-gathered.
+A "step" = every GPU multiplies its own `batch` ciphertext pairs, RAW operands resident in HBM -> RAW products in
+HBM (crt x2, forward NTT x2L, fused pointwise mul + inverse NTT, reduction modulo Phi_m, ICRT).  With N > 1 the
+CRT-residue axis of all batch x N products is sharded (rank r owns primes r, r+N, ...): after CRT an NCCL
+send/recv exchange hands every rank the rows of its primes, before ICRT a second one returns the product rows to the
+owners (cuhe_mul_raw_sharded_batch, exchange inside the library).  One step's result is checked against an
+unsharded context on the same GPU outside the timed region ("verified").
 """
 from __future__ import annotations
 
@@ -34,6 +34,8 @@ sys.path.insert(0, ROOT)
 WORKLOAD = (24, 2, 16, 24, 24, 32767)      # setParameters(d,p,w,min,cut,m): N=65536, L=24, W=18
 WORKLOAD_NAME = "ctxt x ctxt multiply, ring degree 2^15 (n=27000, nttLen=65536), 24 CRT primes (576-bit q)"
 NTT_BYTES_64K = 655360                      # u32[32768] in + u64[65536] out
+WORKLOAD_C5 = (64, 2, 16, 24, 24, 32767)   # BASELINE configs[4]: N=65536, L=64 (8 per GPU at 8 GPUs), W=48
+WORKLOAD_C5_NAME = "batched ctxt x ctxt multiply, n=27000 (nttLen=65536), 64 CRT primes (1536-bit q), residues sharded over the GPUs"
 
 
 def peaks():
@@ -225,6 +227,49 @@ def run_reference(args):
 # --------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------
+def measure_ntt_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the two NTT pass kernels for one batched forward 64K launch pair
+    (batch 512), measured NOW by an `ncu --metrics` child over tools/ntt_bench.py --one (caches left as the preceding
+    launches leave them, clocks untouched).  Returns (bytes per launch pair, source string) or (None, why)."""
+    import shutil
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None, "ncu not found"
+    log = os.path.join("/tmp", f"cuhe_b200_ncu_{os.getpid()}.csv")
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "--cache-control", "none",
+           "-k", "regex:ntt96_pass", "-s", "8", "-c", "4", "--csv", "--log-file", log,
+           sys.executable, os.path.join(ROOT, "tools", "ntt_bench.py"), "--one"]
+    try:
+        subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+        import csv
+        tot, per = 0.0, {}
+        with open(log) as f:
+            rows = [r for r in csv.reader(f) if len(r) > 14 and r[0].isdigit()]
+        for r in rows:
+            val = float(r[14].replace(",", ""))
+            unit = r[13].lower()
+            val *= {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1)
+            per[r[0]] = per.get(r[0], 0.0) + val
+            tot += val
+        os.remove(log)
+        if len(per) != 4:
+            return None, f"ncu captured {len(per)} launches"
+        return int(tot / 2), "measured in this run: ncu --metrics dram__bytes_{read,write}.sum --cache-control none over 2 launch pairs"
+    except Exception as ex:                                      # noqa: BLE001
+        return None, repr(ex)[:200]
+
+
+def make_context(lib, check, cuhe_params, workload, local, rank, world):
+    from cuhe_b200.hostmath import cyclotomic
+    par = cuhe_params()
+    check(lib.cuhe_set_parameters(C.byref(par), *workload))
+    h = C.c_void_p()
+    check(lib.cuhe_ctx_create(C.byref(h), C.byref(par), local, rank, world))
+    phi = np.array(cyclotomic(workload[5]), dtype=np.int64)          # the caller supplies polyMod, as DHS.cu does
+    check(lib.cuhe_ctx_set_poly_modulus_host(h, phi.ctypes.data_as(C.c_void_p), len(phi)))
+    return h, par
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -243,167 +288,180 @@ def run_ours(args):
             os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL prints its banner there)
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=90))   # fail fast on a mismatch
     lib = load_library()
-    par = cuhe_params()
-    check(lib.cuhe_set_parameters(C.byref(par), *WORKLOAD))
-    h = C.c_void_p()
-    check(lib.cuhe_ctx_create(C.byref(h), C.byref(par), local, rank, world))
-    # Phi_m from the host helper (the caller supplies polyMod, as DHS.cu does)
-    from cuhe_b200.hostmath import cyclotomic
-    phi = np.array(cyclotomic(WORKLOAD[5]), dtype=np.int64)
-    check(lib.cuhe_ctx_set_poly_modulus_host(h, phi.ctypes.data_as(C.c_void_p), len(phi)))
-    L, W, H, N, n = par.numCrtPrime, lib.cuhe_param_words_coeff(C.byref(par), 0), par.crtLen, par.nttLen, par.modLen
-    rows = lib.cuhe_ctx_rows(h, 0)
-    assert L % world == 0, "bench shards need numCrtPrime divisible by the GPU count"
-    qw = np.zeros(W + 1, dtype=np.uint32)
-    check(lib.cuhe_ctx_coeff_modulus_host(h, 0, qw.ctypes.data_as(C.c_void_p), W + 1))
-    info = dict(q0=int.from_bytes(qw.tobytes(), "little"), W=W, H=H, n=n)
-    # per-GPU work is held constant: every step multiplies batch*world ciphertext pairs, the residue
-    # axis of all of them sharded over the ranks (weak scaling; the all-gather grows with the batch)
-    B = args.batch * world
-    NBUF = 4 if B <= 64 else 2      # rotating operand sets (each is B x 4.7 MB on the host and on the device)
-    a_np, b_np = gen_raw(info, B, NBUF, 20260924)
-    a_dev = torch.from_numpy(a_np.view(np.int32)).to(dev)
-    b_dev = torch.from_numpy(b_np.view(np.int32)).to(dev)
-    from cuhe_b200 import sharded as sh
-    crt_loc = torch.zeros((B, rows, H), dtype=torch.int32, device=dev)
-    raw_out = torch.zeros((B, H, W), dtype=torch.int32, device=dev)
-    cb, ce = sh.coefficient_slice(H, rank, world)
-    raw_slice = torch.zeros((B, ce - cb, W), dtype=torch.int32, device=dev)
     st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)  # noqa: E731
     p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
 
-    # CUHE_B200_OVERLAP=1 (multi-GPU, not measured yet, off by default): the batch is processed as two halves
-    # on two streams, so that the collectives of one half run under the kernels of the other
-    overlap = world > 1 and os.environ.get("CUHE_B200_OVERLAP") == "1" and B >= 2
-    if overlap:
-        halves = [(0, B // 2), (B // 2, B)]
-        side = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
-
-    def step_overlapped(k):
-        cur = torch.cuda.current_stream()
-        outs = []
-        for s_, (lo_, up_) in zip(side, halves):
-            s_.wait_stream(cur)
-            with torch.cuda.stream(s_):
-                nb = up_ - lo_
-                check(lib.cuhe_mul_crt_batch(h, p(crt_loc[lo_:up_]), p(a_dev[k][lo_:up_]), p(b_dev[k][lo_:up_]), 0, nb, st()))
-                crt_slice = sh.exchange_for_icrt(crt_loc[lo_:up_], L, rank, world)
-                check(lib.cuhe_icrt_slice_batch(h, p(raw_slice[lo_:up_]), p(crt_slice), 0, cb, ce - cb, nb, st()))
-                outs.append(sh.all_gather_raw_slices(raw_slice[lo_:up_], world))
-        for s_ in side:
-            cur.wait_stream(s_)
-        return outs
-
-    def step(i):
-        k = i % NBUF
-        if overlap:
-            return step_overlapped(k)
-        check(lib.cuhe_mul_crt_batch(h, p(crt_loc), p(a_dev[k]), p(b_dev[k]), 0, B, st()))
-        if world == 1:
-            check(lib.cuhe_icrt_batch(h, p(raw_out), p(crt_loc), 0, 0, H, B, st()))
-        else:
-            # NCCL all-to-all over NVLink: rank j receives coefficient slice j of every residue
-            crt_slice = sh.exchange_for_icrt(crt_loc, L, rank, world)
-            check(lib.cuhe_icrt_slice_batch(h, p(raw_slice), p(crt_slice), 0, cb, ce - cb, B, st()))
-            return sh.all_gather_raw_slices(raw_slice, world)            # complete RAW on every rank
+    def join_comm(h):
+        """rank 0 draws the NCCL id, torch.distributed carries the 128 bytes, every rank joins (cuhe_ctx_comm_init)"""
+        idbuf = (C.c_ubyte * 128)()
+        if rank == 0:
+            check(lib.cuhe_comm_unique_id(idbuf))
+        t = torch.tensor(list(idbuf), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, src=0)
+        check(lib.cuhe_ctx_comm_init(h, (C.c_ubyte * 128)(*t.cpu().tolist())))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def setup(workload, batch):
+        """context (residue shard `rank` of `world`), the own operands of this rank and the step function.
+        One step = every rank multiplies its own `batch` ciphertext pairs, RAW in HBM -> RAW in HBM; with world > 1
+        the residue axis of all batch*world products is spread over the ranks inside cuhe_mul_raw_sharded_batch."""
+        h, par = make_context(lib, check, cuhe_params, workload, local, rank, world)
+        if world > 1:
+            join_comm(h)
+        L, W, H, N, n = par.numCrtPrime, lib.cuhe_param_words_coeff(C.byref(par), 0), par.crtLen, par.nttLen, par.modLen
+        qw = np.zeros(W + 1, dtype=np.uint32)
+        check(lib.cuhe_ctx_coeff_modulus_host(h, 0, qw.ctypes.data_as(C.c_void_p), W + 1))
+        info = dict(q0=int.from_bytes(qw.tobytes(), "little"), W=W, H=H, n=n)
+        nbuf = 4 if batch <= 64 else 2      # rotating operand sets
+        a_np, b_np = gen_raw(info, batch, nbuf, 20260924 + rank)
+        a_dev = torch.from_numpy(a_np.view(np.int32)).to(dev)
+        b_dev = torch.from_numpy(b_np.view(np.int32)).to(dev)
+        raw_out = torch.zeros((batch, H, W), dtype=torch.int32, device=dev)
+        crt_loc = torch.zeros((batch, L, H), dtype=torch.int32, device=dev) if world == 1 else None
+
+        def step(i):
+            k = i % nbuf
+            if world == 1:
+                check(lib.cuhe_mul_crt_batch(h, p(crt_loc), p(a_dev[k]), p(b_dev[k]), 0, batch, st()))
+                check(lib.cuhe_icrt_batch(h, p(raw_out), p(crt_loc), 0, 0, H, batch, st()))
+            else:
+                check(lib.cuhe_mul_raw_sharded_batch(h, p(raw_out), p(a_dev[k]), p(b_dev[k]), 0, batch, st()))
+        return dict(h=h, par=par, L=L, W=W, H=H, N=N, n=n, nbuf=nbuf, a_np=a_np, b_np=b_np, a_dev=a_dev, b_dev=b_dev,
+                    raw_out=raw_out, step=step, workload=workload, batch=batch)
+
+    def verify(S):
+        """outside the timed region: the sharded result of this rank's products against a private unsharded context
+        on the same GPU, word for word; AND over the ranks"""
+        if world == 1:
+            return None
+        hu, _ = make_context(lib, check, cuhe_params, S["workload"], local, 0, 1)
+        nb = min(S["batch"], 4)
+        crt_u = torch.zeros((nb, S["L"], S["H"]), dtype=torch.int32, device=dev)
+        out_u = torch.zeros((nb, S["H"], S["W"]), dtype=torch.int32, device=dev)
+        S["step"](0)
+        check(lib.cuhe_mul_crt_batch(hu, p(crt_u), p(S["a_dev"][0]), p(S["b_dev"][0]), 0, nb, st()))
+        check(lib.cuhe_icrt_batch(hu, p(out_u), p(crt_u), 0, 0, S["H"], nb, st()))
+        torch.cuda.synchronize()
+        ok = torch.tensor([1 if torch.equal(out_u, S["raw_out"][:nb]) else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        lib.cuhe_ctx_destroy(hu)
+        del crt_u, out_u
+        return bool(ok.item())
+
+    def timed(S, steps, warmup):
+        for i in range(warmup):
+            S["step"](i)
+        barrier()
+        lib.cuhe_launch_count(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(steps):
+            S["step"](i)
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        return ms, int(lib.cuhe_launch_count(0))
+
+    S = setup(WORKLOAD, args.batch)
+    h, L, W, H, N = S["h"], S["L"], S["W"], S["H"], S["N"]
+    B = args.batch * world
+    verified = verify(S)
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     for i in range(args.warmup):
-        step(i)
+        S["step"](i)
     barrier()
     if rank == 0:
         t_wait = time.time()
         while not sampler.rows and time.time() - t_wait < 5.0:    # nvidia-smi needs ~1 s to print its first row
             time.sleep(0.05)
     barrier()
-    for i in range(args.warmup):                                   # every rank: the steps contain collectives
-        step(i)
-    barrier()
     first_sample = len(sampler.rows)
-    lib.cuhe_launch_count(1)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        step(i)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = int(lib.cuhe_launch_count(0))
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms, launches = timed(S, args.steps, args.warmup)
     value = B * args.steps / (ms * 1e-3)
     clocks = None
     # keep every GPU under the same load for ~0.4 s more so the 50 ms clock samples cover it; the
     # step count is derived from the all-reduced time, hence identical on every rank (collectives inside)
     n_extra = min(2000, max(4, int(400.0 / max(ms / args.steps, 1e-3))))
     for i in range(n_extra):
-        step(i)
+        S["step"](i)
     barrier()
     if rank == 0:
         sampler.rows = sampler.rows[first_sample:]
         clocks = sampler.stop()
 
-    # ---- roofline: the dominant kernels are the NTT passes; time one batched forward
-    #      64K ext-NTT launch pair (pass 1 + pass 2) alone, inputs larger than L2 ----
+    # ---- roofline: the dominant kernels are the NTT passes; every rank times one batched forward 64K ext-NTT launch
+    #      pair (pass 1 + pass 2) alone, at the same time, inputs larger than L2; the rate is summed over the ranks ----
+    cnt = 512
+    src = torch.randint(0, 2**31 - 1, (2, cnt, H), dtype=torch.int32, device=dev)     # 2 x 67 MB
+    dst = torch.zeros((cnt, N), dtype=torch.int64, device=dev)                         # 268 MB
+    for i in range(3):
+        check(lib.cuhe_ntt_ext_batch(h, p(dst), p(src[i % 2]), N, cnt, C.c_longlong(H), st()))
+    barrier()
+    reps = 10
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for i in range(reps):
+        check(lib.cuhe_ntt_ext_batch(h, p(dst), p(src[i % 2]), N, cnt, C.c_longlong(H), st()))
+    k1.record()
+    torch.cuda.synchronize()
+    kms = max_over_ranks(k0.elapsed_time(k1) / reps)
+    del src, dst
+    pk, pk_src = peaks()
+    ach = NTT_BYTES_64K * cnt / (kms * 1e-3) / 1e9
+    ntt_rate = world * cnt / (kms * 1e-3)
     roof = None
-    ntt_rate = None
     if rank == 0:
-        cnt = 512
-        src = torch.randint(0, 2**31 - 1, (2, cnt, H), dtype=torch.int32, device=dev)     # 2 x 67 MB
-        dst = torch.zeros((cnt, N), dtype=torch.int64, device=dev)                         # 268 MB
-        for i in range(3):
-            check(lib.cuhe_ntt_ext_batch(h, p(dst), p(src[i % 2]), N, cnt, C.c_longlong(H), st()))
-        torch.cuda.synchronize()
-        reps = 10
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k0.record()
-        for i in range(reps):
-            check(lib.cuhe_ntt_ext_batch(h, p(dst), p(src[i % 2]), N, cnt, C.c_longlong(H), st()))
-        k1.record()
-        torch.cuda.synchronize()
-        kms = k0.elapsed_time(k1) / reps
-        pk, pk_src = peaks()
-        ach = NTT_BYTES_64K * cnt / (kms * 1e-3) / 1e9
-        ntt_rate = cnt / (kms * 1e-3)
-        roof = {"kernel": "ntt_pass1_v2_kernel<EXT_U32> + ntt_pass2_v2_kernel<16,U64> (one batched forward 64K NTT)",
+        traffic, traffic_src = (None, "skipped (--no-cpu / multi-GPU run)")
+        if world == 1 and not args.no_cpu:
+            traffic, traffic_src = measure_ntt_traffic()
+        if traffic is None:
+            try:
+                t = json.load(open(os.path.join(ROOT, "profiles", "ntt_traffic.json")))
+                traffic, traffic_src = t["dram_bytes_per_launch_pair"], "committed capture " + t["source"] + " (live measurement: " + traffic_src + ")"
+            except Exception:
+                pass
+        roof = {"kernel": "ntt96_pass1_kernel<1024, EXT_U32> + ntt96_pass2_kernel<16, 4, U64> (one batched forward 64K NTT, per GPU)",
                 "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-                "peak_source": pk_src + " (burst copy bandwidth)", "traffic": ntt_traffic(cnt),
+                "peak_source": pk_src + " (burst copy bandwidth)", "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": NTT_BYTES_64K * cnt, "launch_ms": kms, "batch": cnt,
-                "secondary": ntt_issue(cnt, kms),
-                "note": "INT32-ALU bound (SURVEY F9): see DESIGN.md for the instruction-issue roofline"}
-        del src, dst
+                "secondary": {"bound": "instruction issue / int32 alu pipe: ~205 SASS instructions per point, ~70 % of them on the alu pipe "
+                                       "(64 lanes/clk/SM); measured issue ceiling with both pipes busy 105 thread-instr/clk/SM "
+                                       "(profiles/r02_pipe_issue_rates.txt)",
+                              "thread_instr_per_point": 205, "issue_ceiling_ntt_per_s_per_gpu": 148 * 1.965e9 * 105 / (205 * 65536)},
+                "note": "ALU-pipe / issue bound, not HBM bound (SURVEY F9); DESIGN.md section 4.2"}
 
-    # ---- e2e: host buffers through the C ABI (the device part of mulZZX), H2D + D2H inside ----
+    # ---- e2e: host buffers, H2D + D2H inside the timed region ----
     e2e = None
     if world > 1:
-        # data-parallel host side: rank r owns products [r*b, (r+1)*b) of every step.  Per step and rank:
-        # H2D of the owned operands from pinned memory -> NVLink all-gather of the RAW operands -> the
-        # residue-sharded multiply (all-to-all, sliced ICRT) -> all-to-all of RAW slices back to the
-        # owners -> D2H of the owned products.  Every polynomial crosses PCIe once per step in the whole
-        # job.  Copies run on side streams, double buffered, so step i+1's upload and step i-1's download
-        # overlap step i's kernels and collectives.
+        # every rank: pinned host RAW of its own products -> H2D -> cuhe_mul_raw_sharded_batch (exchange inside the
+        # library) -> D2H of its own products.  Copies on side streams, double buffered, under the neighbouring steps.
         b = args.batch
-        lo = rank * b
-        ah = [torch.from_numpy(a_np[k][lo:lo + b].view(np.int32)).pin_memory() for k in range(2)]
-        bh = [torch.from_numpy(b_np[k][lo:lo + b].view(np.int32)).pin_memory() for k in range(2)]
+        a_np, b_np = S["a_np"], S["b_np"]
+        ah = [torch.from_numpy(a_np[k].view(np.int32)).pin_memory() for k in range(2)]
+        bh = [torch.from_numpy(b_np[k].view(np.int32)).pin_memory() for k in range(2)]
         oh = [torch.zeros((b, H, W), dtype=torch.int32).pin_memory() for _ in range(2)]
         a_loc = [torch.zeros((b, H, W), dtype=torch.int32, device=dev) for _ in range(2)]
         b_loc = [torch.zeros((b, H, W), dtype=torch.int32, device=dev) for _ in range(2)]
-        o_loc = [None, None]
+        o_loc = [torch.zeros((b, H, W), dtype=torch.int32, device=dev) for _ in range(2)]
         s_in, s_comp, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         ev_in = [torch.cuda.Event() for _ in range(2)]          # operands of slot k are on the device
-        ev_used = [torch.cuda.Event() for _ in range(2)]        # slot k's operands have been gathered
-        ev_done = [torch.cuda.Event() for _ in range(2)]        # slot k's owned products are in o_loc[k]
+        ev_used = [torch.cuda.Event() for _ in range(2)]        # slot k's operands have been consumed
+        ev_done = [torch.cuda.Event() for _ in range(2)]        # slot k's products are in o_loc[k]
         ev_read = [torch.cuda.Event() for _ in range(2)]        # slot k's products have left the device
 
         def upload(i):
@@ -419,15 +477,10 @@ def run_ours(args):
             k = i % 2
             with torch.cuda.stream(s_comp):
                 s_comp.wait_event(ev_in[k])
-                a_all = sh.all_gather_operands(a_loc[k], world)
-                b_all = sh.all_gather_operands(b_loc[k], world)
-                ev_used[k].record(s_comp)
-                check(lib.cuhe_mul_crt_batch(h, p(crt_loc), p(a_all), p(b_all), 0, B, st()))
-                crt_slice = sh.exchange_for_icrt(crt_loc, L, rank, world)
-                check(lib.cuhe_icrt_slice_batch(h, p(raw_slice), p(crt_slice), 0, cb, ce - cb, B, st()))
                 if i >= 2:
                     s_comp.wait_event(ev_read[k])
-                o_loc[k] = sh.raw_slices_to_owners(raw_slice, world)
+                check(lib.cuhe_mul_raw_sharded_batch(h, p(o_loc[k]), p(a_loc[k]), p(b_loc[k]), 0, b, st()))
+                ev_used[k].record(s_comp)
                 ev_done[k].record(s_comp)
 
         def download(i):
@@ -453,18 +506,17 @@ def run_ours(args):
         t0 = time.perf_counter()
         e2e_run(args.steps)
         barrier()
-        el = time.perf_counter() - t0
-        tt = torch.tensor([el], device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": B * args.steps / float(tt.item()), "unit": "mul/s", "h2d_bytes_per_step": int(2 * B * H * W * 4),
+        el = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": B * args.steps / el, "unit": "mul/s", "h2d_bytes_per_step": int(2 * B * H * W * 4),
                "d2h_bytes_per_step": int(B * H * W * 4),
-               "api": "each rank: pinned host RAW of its products -> H2D -> NVLink all-gather -> sharded cuhe_mul_crt_batch / "
-                      "all-to-all / cuhe_icrt_slice_batch / all-to-all to owners -> D2H (double-buffered side streams); "
+               "api": "each rank: pinned host RAW of its own products -> H2D -> cuhe_mul_raw_sharded_batch (CRT, NCCL exchange of "
+                      "residue rows, transforms, exchange back, ICRT inside the library) -> D2H (double-buffered side streams); "
                       "byte counts are whole-job totals"}
     if world == 1:
         # one e2e step = one call with Be = 4*B products from pinned host memory; the library pipelines
-        # H2D | kernels | D2H over chunks of 8 products inside the call
+        # H2D | kernels | D2H over chunks of products inside the call
         Be = 4 * B
+        a_np, b_np, NBUF = S["a_np"], S["b_np"], S["nbuf"]
         ah = torch.from_numpy(np.concatenate([a_np[i % NBUF] for i in range(4)]).view(np.int32)).pin_memory()
         bh = torch.from_numpy(np.concatenate([b_np[i % NBUF] for i in range(4)]).view(np.int32)).pin_memory()
         oh = torch.zeros((Be, H, W), dtype=torch.int32).pin_memory()
@@ -479,6 +531,26 @@ def run_ours(args):
         e2e = {"value": Be * args.steps / el, "unit": "mul/s", "h2d_bytes_per_step": int(2 * Be * H * W * 4),
                "d2h_bytes_per_step": int(Be * H * W * 4), "batch": Be,
                "api": "cuhe_mul_raw_host_batch (pinned host RAW in/out, 3-stream pipeline inside the call)"}
+        del ah, bh, oh
+
+    # ---- BASELINE configs[4]: batched multiply at 64 CRT primes (1536-bit q), residues over the ranks (8 per GPU at N = 8);
+    #      same step definition, fewer steps.  Reported beside the headline so that every N has both workloads. ----
+    config5 = None
+    if not args.no_c5:
+        for key in ("a_dev", "b_dev", "raw_out", "a_np", "b_np"):
+            S.pop(key, None)
+        lib.cuhe_ctx_destroy(h)
+        torch.cuda.empty_cache()
+        b5 = max(1, args.batch // 4)
+        S5 = setup(WORKLOAD_C5, b5)
+        ok5 = verify(S5)
+        steps5 = max(3, args.steps // 2)
+        ms5, _ = timed(S5, steps5, 3)
+        config5 = {"workload": WORKLOAD_C5_NAME, "value": b5 * world * steps5 / (ms5 * 1e-3), "unit": "mul/s", "batch_per_gpu": b5,
+                   "residues_per_gpu": S5["L"] // world if S5["L"] % world == 0 else f"{S5['L']}/{world}", "ms_per_step": ms5 / steps5,
+                   "steps": steps5, "verified": ok5}
+        lib.cuhe_ctx_destroy(S5["h"])
+        h = None
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -500,19 +572,38 @@ def run_ours(args):
         # configs[0] latency.  Isolated in a child process so that nothing it does can disturb this line.
         sweep = child_json("ntt_bench.py", "--sweep")
 
+    # ---- the reference interface itself: cuHE::mulZZX (ZZX in, ZZX out; cuhe/CuHE.cu:259-268) through libcuhe_compat.so,
+    #      one call per product, host threads on their own streams (tools/mulzzx_bench.cpp, child process) ----
+    mulzzx = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        exe = os.path.join(ROOT, "tools", "_mulzzx_bench")
+        if os.path.exists(exe):
+            try:
+                nthreads = str(min(16, max(2, _host_threads())))
+                r = subprocess.run([exe, nthreads, "24"], capture_output=True, text=True, timeout=240)
+                lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+                mulzzx = json.loads(lines[-1]) if lines else {"error": (r.stdout + r.stderr)[-300:]}
+            except Exception as ex:                              # noqa: BLE001
+                mulzzx = {"error": repr(ex)[:300]}
+        else:
+            mulzzx = {"error": "tools/_mulzzx_bench not built"}
+
     if rank == 0:
         out = {
             "metric": "homomorphic ctxt x ctxt mul/s", "value": value, "unit": "mul/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64 (mod 2^64-2^32+1) / u32 residues",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD_NAME, "batch": B, "batch_per_gpu": args.batch, "parallelism": f"residue-shard x{world}" if world > 1 else "single GPU",
-                       "l2": f"{NBUF} rotating operand sets; per-step NTT intermediates {2 * B * L * N * 8 / 1e6:.0f} MB exceed the 126 MB L2"},
-            "ntt_64k_per_s": ntt_rate, "ntt_sweep": sweep, "relin_config3": relin3, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-            "clocks": clocks,
+            "config": {"workload": WORKLOAD_NAME, "batch": B, "batch_per_gpu": args.batch,
+                       "parallelism": f"residue-shard x{world}: every rank owns {args.batch} products, residue rows exchanged by NCCL send/recv "
+                                      "inside cuhe_mul_raw_sharded_batch" if world > 1 else "single GPU",
+                       "l2": f"{S['nbuf']} rotating operand sets; per-step NTT intermediates {2 * B * L * N * 8 / world / 1e6:.0f} MB per GPU exceed the 126 MB L2"},
+            "verified": verified, "ntt_64k_per_s": ntt_rate, "ntt_sweep": sweep, "relin_config3": relin3, "config5": config5,
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "e2e_mulzzx": mulzzx, "gpu_launches": launches, "clocks": clocks,
         }
         print(json.dumps(out))
-    lib.cuhe_ctx_destroy(h)
+    if h is not None:
+        lib.cuhe_ctx_destroy(h)
     if world > 1:
         dist.destroy_process_group()
 
@@ -524,7 +615,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=32, help="ciphertext pairs per step and per GPU (32: 9.0 k mul/s, 8: 7.9 k)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / relin / sweep / live ncu traffic legs")
+    ap.add_argument("--no-c5", action="store_true", help="skip the BASELINE configs[4] leg (64 primes)")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 40:

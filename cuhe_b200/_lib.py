@@ -69,6 +69,9 @@ SYMBOLS = {
     "cuhe_mod_switch": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
     "cuhe_relin_init": (_i, [_vp, _vp, _vp]),
     "cuhe_relin": (_i, [_vp, _vp, _vp, _i, _vp]),
+    "cuhe_relin_key_words": (C.c_size_t, [_vp]),
+    "cuhe_relin_export_host": (_i, [_vp, _vp, C.c_size_t, _vp]),
+    "cuhe_relin_import_host": (_i, [_vp, _vp, C.c_size_t, _vp]),
     "cuhe_ntt_ext_batch": (_i, [_vp, _vp, _vp, _i, _i, _ll, _vp]),
     "cuhe_intt_batch": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "cuhe_mul_raw_host": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),

@@ -70,9 +70,22 @@ _evalkeys_loaded = False
 
 
 def _stream_ptr(st, dev):
-    if st is None:
-        st = torch.cuda.current_stream(dev)
+    """Stream handle for a launch.  An explicit stream that is not torch's current one is first ordered after the
+    current stream: the buffers of an operation are allocated and zero-filled there (rRepCreate / cRepCreate /
+    nRepCreate), and the kernel must not overtake the fill."""
+    cur = torch.cuda.current_stream(dev)
+    if st is None or st.cuda_stream == cur.cuda_stream:
+        return C.c_void_p(cur.cuda_stream)
+    st.wait_stream(cur)
     return C.c_void_p(st.cuda_stream)
+
+
+def _after(st, dev):
+    """End of an operation on an explicit stream: block until it drains, as the reference does after every
+    operation (cudaStreamSynchronize(st), cuhe/CuHE.cu:81-268), so that inputs dropped right afterwards
+    (rRepFree / cRepFree / nRepFree hand the memory back to torch's allocator) are no longer in use."""
+    if st is not None and st.cuda_stream != torch.cuda.current_stream(dev).cuda_stream:
+        st.synchronize()
 
 
 def _ptr(t: torch.Tensor):
@@ -329,6 +342,7 @@ class CuPolynomial:
             with torch.cuda.device(self.device_):
                 check(load_library().cuhe_crt(ctx(self.device_), _ptr(self.cRep_), _ptr(self.rRep_), self._lvl(),
                                               _stream_ptr(st, self.device_)))
+                _after(st, self.device_)
             self.rRepFree()
         else:
             self.cRep_ = self.rRep_.reshape(1, param.crtLen)
@@ -342,6 +356,7 @@ class CuPolynomial:
             with torch.cuda.device(self.device_):
                 check(load_library().cuhe_icrt(ctx(self.device_), _ptr(self.rRep_), _ptr(self.cRep_), self._lvl(), 0,
                                                param.crtLen, _stream_ptr(st, self.device_)))
+                _after(st, self.device_)
             self.cRepFree()
         else:
             self.rRep_ = self.cRep_.reshape(param.rawLen, 1)
@@ -356,6 +371,7 @@ class CuPolynomial:
             # a plaintext (logq <= logCrtPrime) is level -1: one residue (cuhe/Parameters.cu:107-109)
             check(lib.cuhe_ntt(ctx(self.device_), _ptr(self.nRep_), _ptr(self.cRep_), self._lvl(),
                                _stream_ptr(st, self.device_)))
+            _after(st, self.device_)
         self.cRepFree()
         self.domain_ = 3
 
@@ -366,6 +382,7 @@ class CuPolynomial:
         with torch.cuda.device(self.device_):
             fn = lib.cuhe_intt_mod if self.isProd_ else lib.cuhe_intt
             check(fn(ctx(self.device_), _ptr(self.cRep_), _ptr(self.nRep_), self._lvl(), _stream_ptr(st, self.device_)))
+            _after(st, self.device_)
         self.isProd_ = False
         self.nRepFree()
         self.domain_ = 2
@@ -459,6 +476,7 @@ class CuCtxt(CuPolynomial):
         with torch.cuda.device(self.device_):
             check(load_library().cuhe_mod_switch(ctx(self.device_), _ptr(self.cRep_), _ptr(self.cRep_),
                                                  _ptr(self.cRep_[L - 1]), self.level_, _stream_ptr(st, self.device_)))
+            _after(st, self.device_)
         self.cRep_ = self.cRep_[:L - 1]
         self.logq_ -= param.logCoeffCut
         self.level_ += 1
@@ -486,6 +504,7 @@ class CuCtxt(CuPolynomial):
         with torch.cuda.device(self.device_):
             check(load_library().cuhe_relin(ctx(self.device_), _ptr(self.nRep_), _ptr(self.rRep_), self.level_,
                                             _stream_ptr(st, self.device_)))
+            _after(st, self.device_)
         self.rRepFree()
         self.isProd_ = True
         self.domain_ = 3
@@ -560,6 +579,7 @@ def cAnd(out: CuCtxt, in0: CuCtxt, in1, st=None):
     with torch.cuda.device(out.device()):
         check(fn(ctx(out.device()), _ptr(out.nRep_), _ptr(in0.nRep_), _ptr(in1.nRep_), out.level(),
                  _stream_ptr(st, out.device())))
+        _after(st, out.device())
     out.isProd(True)
 
 
@@ -586,6 +606,7 @@ def cXor(out: CuCtxt, in0: CuCtxt, in1, st=None):
         else:
             fn = lib.cuhe_ntt_add_nx1 if is_ptxt else lib.cuhe_ntt_add
             check(fn(ctx(out.device()), _ptr(out.nRep_), _ptr(in0.nRep_), _ptr(in1.nRep_), out.level(), s))
+        _after(st, out.device())
 
 
 def cNot(out: CuCtxt, inp: CuCtxt, st=None):
@@ -599,6 +620,7 @@ def cNot(out: CuCtxt, inp: CuCtxt, st=None):
     with torch.cuda.device(out.device()):
         check(load_library().cuhe_crt_add_int(ctx(out.device()), _ptr(out.cRep_), _ptr(inp.cRep_),
                                               C.c_uint(param.modMsg - 1), out.level(), _stream_ptr(st, out.device())))
+        _after(st, out.device())
 
 
 def moveTo(tar: CuCtxt, dstDev: int, st=None):

@@ -915,6 +915,35 @@ int cuhe_relin_init(cuhe_ctx* c, const uint32_t* evalkeys_raw, cuhe_stream strea
     });
 }
 
+// ---- evaluation keys in the form the key switch consumes (u64[rows(0)][numEvalKey][nttLen], NTT domain): export
+//      after cuhe_relin_init, import instead of it -- the binary RNS key format of cuhe_utils / utils.py carries them
+size_t cuhe_relin_key_words(const cuhe_ctx* c) {
+    if (!c || c->par.logRelin <= 0) return 0;
+    return (size_t)c->rows(0) * c->par.numEvalKey * c->par.nttLen;
+}
+int cuhe_relin_export_host(cuhe_ctx* c, uint64_t* out_host, size_t words, cuhe_stream stream) {
+    return guarded([&] {
+        REQUIRE(c && out_host, "null argument");
+        if (!c->d_ek) throw StateError{"cuhe_relin_init / cuhe_relin_import_host has not been called"};
+        REQUIRE(words == cuhe_relin_key_words(c), "word count differs from cuhe_relin_key_words");
+        DeviceGuard dg(c->device);
+        CK(cudaMemcpyAsync(out_host, c->d_ek, words * 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        CK(cudaStreamSynchronize((cudaStream_t)stream));
+    });
+}
+int cuhe_relin_import_host(cuhe_ctx* c, const uint64_t* in_host, size_t words, cuhe_stream stream) {
+    return guarded([&] {
+        REQUIRE(c && in_host, "null argument");
+        REQUIRE(c->par.logRelin > 0 && c->par.numEvalKey > 0, "parameters have no relinearization (w = 0)");
+        REQUIRE(words == cuhe_relin_key_words(c), "word count differs from cuhe_relin_key_words");
+        DeviceGuard dg(c->device);
+        if (c->d_ek) { cudaFree(c->d_ek); c->d_ek = nullptr; }
+        CK(cudaMalloc(&c->d_ek, std::max<size_t>(1, words * 8)));
+        CK(cudaMemcpyAsync(c->d_ek, in_host, words * 8, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+        CK(cudaStreamSynchronize((cudaStream_t)stream));
+    });
+}
+
 int cuhe_relin(cuhe_ctx* c, uint64_t* dst, const uint32_t* raw, int lvl, cuhe_stream stream) {
     return guarded([&] {
         check_lvl(c, lvl); REQUIRE(dst && raw, "null pointer");
@@ -1036,11 +1065,21 @@ int cuhe_mul_raw_host_batch(cuhe_ctx* c, uint32_t* out_h, const uint32_t* a_h, c
         cudaStream_t st = (cudaStream_t)stream;
         const int L = c->L(lvl), W = c->par.wordsCoeffAt(lvl), H = c->par.crtLen;
         const size_t poly_w = (size_t)H * W;                 // words per RAW polynomial
-        if (!c->s_h2d) {
-            CK(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
-            CK(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
-            CK(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+        {
+            std::lock_guard<std::mutex> lk(c->mu);
+            if (!c->s_h2d) {
+                CK(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+                CK(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
+                CK(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+            }
         }
+        // events are destroyed on every exit path (after the buffers and the drain guard declared below)
+        struct Events {
+            std::vector<cudaEvent_t> ev;
+            cuhe_ctx* c;
+            ~Events() { for (auto& e : ev) if (e) cudaEventDestroy(e); }
+            cudaEvent_t make() { cudaEvent_t e = nullptr; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ev.push_back(e); return e; }
+        } evs{{}, c};
         // three-stage pipeline over chunks of the batch: H2D | compute | D2H on separate streams, so
         // PCIe transfers in both directions overlap the kernels (the reference's z2r/r2z are
         // synchronous per polynomial, cuhe/CuHE.cu:317-348)
@@ -1062,18 +1101,23 @@ int cuhe_mul_raw_host_batch(cuhe_ctx* c, uint32_t* out_h, const uint32_t* a_h, c
             if (tail) sizes.push_back(tail);
         }
         const int nchunk = (int)sizes.size();
-        cudaEvent_t ready;
-        CK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+        cudaEvent_t ready = evs.make();
         CK(cudaEventRecord(ready, st));                      // order after the caller's stream
         CK(cudaStreamWaitEvent(c->s_h2d, ready, 0));
         CK(cudaStreamWaitEvent(c->s_comp, ready, 0));
         Tmp ra(c, (size_t)batch * poly_w * 4, c->s_comp), rb(c, (size_t)batch * poly_w * 4, c->s_comp);
         Tmp cc(c, (size_t)batch * L * H * 4, c->s_comp), ro(c, (size_t)batch * poly_w * 4, c->s_comp);
+        // declared after the buffers, hence destroyed before them: on EVERY exit (also a failure half way) the three
+        // internal streams are drained before the buffers are released
+        struct Drain {
+            cuhe_ctx* c;
+            ~Drain() { cudaStreamSynchronize(c->s_h2d); cudaStreamSynchronize(c->s_comp); cudaStreamSynchronize(c->s_d2h); }
+        } drain{c};
         CK(cudaEventRecord(ready, c->s_comp));               // buffers exist
         CK(cudaStreamWaitEvent(c->s_h2d, ready, 0));
         CK(cudaMemsetAsync(ro.p, 0, (size_t)batch * poly_w * 4, c->s_comp));
         std::vector<cudaEvent_t> ev(2 * nchunk);
-        for (auto& e : ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : ev) e = evs.make();
         for (int i = 0, b0 = 0; i < nchunk; b0 += sizes[i], i++) {
             const int nb = sizes[i];
             const size_t off = (size_t)b0 * poly_w, bytes = (size_t)nb * poly_w * 4;
@@ -1090,8 +1134,6 @@ int cuhe_mul_raw_host_batch(cuhe_ctx* c, uint32_t* out_h, const uint32_t* a_h, c
         }
         CK(cudaStreamSynchronize(c->s_d2h));
         CK(cudaStreamSynchronize(c->s_comp));
-        for (auto& e : ev) cudaEventDestroy(e);
-        cudaEventDestroy(ready);
     });
 }
 

@@ -160,8 +160,13 @@ struct Params {
         throw std::invalid_argument("lvl cannot be more than depth");
     }
     int wordsCoeffAt(int lvl) const { int t = (logCoeffAt(lvl) + 31) / 32; return t > 1 ? t : 1; }
-    int numEvalKeyAt(int lvl) const { return (logCoeffAt(lvl) + logRelin - 1) / logRelin; }
-    int levelOf(int logq) const { return logq >= logCoeffMin ? (logCoeffMax - logq) / logCoeffCut : -1; }
+    // w = 0 (no relinearization) and cut = 0 (depth 1) are accepted by setParameters; the reference divides by them
+    // (cuhe/Parameters.cu:128-145) and dies with SIGFPE -- here they give 0 keys / level 0
+    int numEvalKeyAt(int lvl) const { return logRelin > 0 ? (logCoeffAt(lvl) + logRelin - 1) / logRelin : 0; }
+    int levelOf(int logq) const {
+        if (logq < logCoeffMin) return -1;
+        return logCoeffCut > 0 ? (logCoeffMax - logq) / logCoeffCut : 0;
+    }
 };
 
 inline Params set_param(int d, int p, int w, int mn, int cut, int m) {

@@ -12,6 +12,8 @@
 #include <exception>
 #include <vector>
 
+#include <omp.h>
+
 #include "../../include/cuhe_b200.h"
 
 namespace cuHE {
@@ -185,6 +187,11 @@ uint64* CuPolynomial::nRep() { return nRep_; }
 int CuPolynomial::coeffWords() { return (logq_ + 31) / 32; }
 size_t CuPolynomial::rRepSize() { return (size_t)param.rawLen * coeffWords() * sizeof(uint32); }
 
+static void zzx_to_raw(uint32* buf, const ZZX& z, int W, int len);
+static void raw_to_zzx(ZZX& z, const uint32* buf, int W, int len);
+static void zzx_to_raw_fwd(uint32* buf, const ZZX& z, int W, int len) { zzx_to_raw(buf, z, W, len); }
+static void raw_to_zzx_fwd(ZZX& z, const uint32* buf, int W, int len) { raw_to_zzx(z, buf, W, len); }
+
 static void* zeroed(int dev, size_t bytes, cudaStream_t st) {          // *RepCreate: allocate + memset (cuhe/CuHE.cu:468-488)
     void* p = nullptr;
     ok(cuhe_malloc(ctx(dev), &p, bytes, st));
@@ -203,8 +210,7 @@ void CuPolynomial::z2r(cudaStream_t st) {                   // cuhe/CuHE.cu:317-
     rRepCreate(st);
     uint32* buf = g_staging[device_];
     const int W = coeffWords();
-    for (int i = 0; i < param.rawLen; i++)
-        NTL::BytesFromZZ((unsigned char*)(buf + (size_t)i * W), coeff(zRepRef(), i), (long)W * sizeof(uint32));
+    zzx_to_raw_fwd(buf, zRepRef(), W, param.rawLen);
     ok(cuhe_memcpy(ctx(device_), rRep_, buf, rRepSize(), 0, st));
     ok(cuhe_stream_sync(ctx(device_), st));
     clear(zRepRef());
@@ -216,9 +222,7 @@ void CuPolynomial::r2z(cudaStream_t st) {                   // cuhe/CuHE.cu:333-
     const int W = coeffWords();
     ok(cuhe_memcpy(ctx(device_), buf, rRep_, rRepSize(), 1, st));
     ok(cuhe_stream_sync(ctx(device_), st));
-    clear(zRepRef());
-    for (int i = 0; i < param.modLen; i++)
-        SetCoeff(zRepRef(), i, NTL::ZZFromBytes((const unsigned char*)(buf + (size_t)i * W), (long)W * sizeof(uint32)));
+    raw_to_zzx_fwd(zRepRef(), buf, W, param.modLen);
     rRepFree();
     domain_ = 0;
 }
@@ -438,15 +442,67 @@ void copyTo(CuCtxt& dst, CuCtxt& src, int dstDev, cudaStream_t st) {
     copy_ref(dst, src, st);
     moveTo(dst, dstDev, st);
 }
-void mulZZX(ZZX& out, ZZX in0, ZZX in1, int lvl, int dev, cudaStream_t st) {   // cuhe/CuHE.cu:259-268
-    CuCtxt cin0, cin1;
-    cin0.setLevel(lvl, dev, in0);
-    cin1.setLevel(lvl, dev, in1);
-    cin0.x2n(st);
-    cin1.x2n(st);
-    cAnd(cin0, cin0, cin1, st);
-    cin0.x2z(st);
-    out = cin0.zRep();
+// ---- ZZX <-> RAW marshalling, parallel over coefficients (the reference's loops are serial,
+//      cuhe/CuHE.cu:324-326,343-345; NTL's BytesFromZZ / ZZFromBytes only touch their own operands) -----------
+static void zzx_to_raw(uint32* buf, const ZZX& z, int W, int len) {
+#pragma omp parallel for schedule(static) if (len >= 4096 && !omp_in_parallel())
+    for (int i = 0; i < len; i++)
+        NTL::BytesFromZZ((unsigned char*)(buf + (size_t)i * W), coeff(z, i), (long)W * sizeof(uint32));
+}
+static void raw_to_zzx(ZZX& z, const uint32* buf, int W, int len) {
+    std::vector<ZZ> tmp((size_t)len);
+#pragma omp parallel for schedule(static) if (len >= 4096 && !omp_in_parallel())
+    for (int i = 0; i < len; i++)
+        tmp[(size_t)i] = NTL::ZZFromBytes((const unsigned char*)(buf + (size_t)i * W), (long)W * sizeof(uint32));
+    clear(z);
+    for (int i = len - 1; i >= 0; i--)            // highest first: one allocation of the coefficient vector
+        if (!IsZero(tmp[(size_t)i])) SetCoeff(z, i, tmp[(size_t)i]);
+}
+// per-thread pinned staging of mulZZX (three RAW polynomials per device), so that host threads can multiply
+// concurrently on their own streams -- the reference's single dhBuffer_ per device allows one call at a time
+namespace {
+struct ThreadStaging {
+    uint32* buf[kMaxDev] = {nullptr};
+    size_t words[kMaxDev] = {0};
+    ~ThreadStaging() { for (int d = 0; d < kMaxDev; d++) if (buf[d]) cuhe_host_free(buf[d]); }
+    uint32* get(int dev, size_t need) {
+        if (words[dev] < need) {
+            if (buf[dev]) cuhe_host_free(buf[dev]);
+            void* p = nullptr;
+            ok(cuhe_host_alloc(&p, need * sizeof(uint32)));
+            buf[dev] = (uint32*)p; words[dev] = need;
+        }
+        return buf[dev];
+    }
+};
+thread_local ThreadStaging t_staging;
+}  // namespace
+
+// cuhe/CuHE.cu:259-268.  The reference walks the CuCtxt state machine (setLevel x2, x2n x2, cAnd, x2z: nine device
+// operations, each followed by a stream synchronisation, two serial marshalling loops in, one out).  Same result
+// through one pipelined call of the C ABI: marshal both operands (parallel loops), cuhe_mul_raw_host (H2D, CRT,
+// transforms, product, inverse, reduction, ICRT, D2H with one synchronisation), unmarshal.
+// CUHE_B200_MULZZX=literal keeps the reference's sequence (A/B; tests cover both).
+void mulZZX(ZZX& out, ZZX in0, ZZX in1, int lvl, int dev, cudaStream_t st) {
+    static const bool literal = [] { const char* e = std::getenv("CUHE_B200_MULZZX"); return e && e[0] == 'l'; }();
+    if (literal) {
+        CuCtxt cin0, cin1;
+        cin0.setLevel(lvl, dev, in0);
+        cin1.setLevel(lvl, dev, in1);
+        cin0.x2n(st);
+        cin1.x2n(st);
+        cAnd(cin0, cin0, cin1, st);
+        cin0.x2z(st);
+        out = cin0.zRep();
+        return;
+    }
+    const int W = param._wordsCoeff(lvl), H = param.rawLen;
+    const size_t poly = (size_t)H * W;
+    uint32* s = t_staging.get(dev, 3 * poly);
+    zzx_to_raw(s, in0, W, H);
+    zzx_to_raw(s + poly, in1, W, H);
+    ok(cuhe_mul_raw_host(ctx(dev), s + 2 * poly, s, s + poly, lvl, st));
+    raw_to_zzx(out, s + 2 * poly, W, param.modLen);
 }
 
 }  // namespace cuHE

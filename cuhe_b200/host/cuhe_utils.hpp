@@ -5,6 +5,7 @@
 // and accessors, so examples/DHS/DHS.cu:57-189 (key import/export) compiles against this header.
 // Pure host code; ZZ/ZZX are NTL's when present, zz_lite's otherwise.
 #pragma once
+#include <cstdint>
 #include <string>
 #include <vector>
 
@@ -61,6 +62,23 @@ private:
     std::vector<Picklable*> items_;
     std::vector<Picklable*> owned_;                         // the ones parse() created
     std::string sep_;
+};
+
+// ---- binary RNS container (no reference counterpart; cuhe/Utils.cu:75-152 only has the decimal text form) ------------
+// Residue-domain data exactly as the device holds it -- CRT domain u32[rows][crtLen] or NTT domain
+// u64[rows][..][nttLen], e.g. the transformed evaluation keys of cuhe_relin_export_host / cuhe_relin_import_host --
+// with the setParameters tuple that fixes its meaning and a checksum.  Same bytes as cuhe_b200/utils.py save_rns /
+// load_rns (80-byte little-endian header "CUHERNS1", see there); files are interchangeable between the two.
+struct RnsBlob {
+    int params[6] = {0, 0, 0, 0, 0, 0};        // d, p, w, min, cut, m
+    int domain = 2;                              // 2 = CRT (u32 elements), 3 = NTT (u64 elements)
+    int level = 0, shard_rank = 0, shard_world = 1;
+    std::vector<uint32_t> dims;                  // 1 to 3 extents
+    std::vector<unsigned char> payload;          // little-endian elements
+
+    static uint64_t checksum(const unsigned char* data, size_t bytes);
+    void save(const std::string& path) const;    // throws std::runtime_error
+    static RnsBlob load(const std::string& path);  // throws std::runtime_error on a damaged file
 };
 
 }  // namespace cuHE_Utils

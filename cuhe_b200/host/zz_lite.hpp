@@ -201,16 +201,14 @@ inline bool IsZero(const ZZ& a) { return a.is_zero(); }
 inline void clear(ZZ& a) { a = ZZ(); }
 // low-order n bytes of |a|, little endian (NTL BytesFromZZ)
 inline void BytesFromZZ(unsigned char* p, const ZZ& a, long n) {
-    std::memset(p, 0, (size_t)n);
-    const std::vector<uint32_t>& l = a.limbs();
-    for (long i = 0; i < n; i++) {
-        const size_t w = (size_t)i / 4;
-        if (w < l.size()) p[i] = (unsigned char)(l[w] >> (8 * (i % 4)));
-    }
+    const std::vector<uint32_t>& l = a.limbs();              // little-endian limbs == little-endian bytes on x86-64
+    const size_t have = l.size() * 4, take = have < (size_t)n ? have : (size_t)n;
+    if (take) std::memcpy(p, l.data(), take);
+    if (take < (size_t)n) std::memset(p + take, 0, (size_t)n - take);
 }
 inline ZZ ZZFromBytes(const unsigned char* p, long n) {
     std::vector<uint32_t> l((size_t)(n + 3) / 4, 0);
-    for (long i = 0; i < n; i++) l[(size_t)i / 4] |= (uint32_t)p[i] << (8 * (i % 4));
+    if (n > 0) std::memcpy(l.data(), p, (size_t)n);
     return ZZ::from_limbs(l);
 }
 

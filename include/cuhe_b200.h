@@ -158,6 +158,12 @@ int cuhe_mod_switch(cuhe_ctx* ctx, uint32_t* dst, const uint32_t* src, const uin
 int cuhe_relin_init(cuhe_ctx* ctx, const uint32_t* evalkeys_raw, cuhe_stream stream);
 /* raw u32[crtLen][words(lvl)] (full polynomial) -> dst u64[rows(lvl)][nttLen] */
 int cuhe_relin(cuhe_ctx* ctx, uint64_t* dst, const uint32_t* raw, int lvl, cuhe_stream stream);
+/* The transformed keys as the key switch consumes them (u64[rows(0)][numEvalKey][nttLen]; the reference keeps the same
+ * data in pinned host memory, h_ek, cuhe/Relinearization.cu:43-56).  Export after cuhe_relin_init, import instead of it:
+ * start-up without CRT / transform work.  The binary RNS container of cuhe_utils.hpp / utils.py stores them on disk. */
+size_t cuhe_relin_key_words(const cuhe_ctx* ctx);
+int cuhe_relin_export_host(cuhe_ctx* ctx, uint64_t* out_host, size_t words, cuhe_stream stream);
+int cuhe_relin_import_host(cuhe_ctx* ctx, const uint64_t* in_host, size_t words, cuhe_stream stream);
 
 /* ---- raw batched transforms, any supported length (16384/32768/65536): the
  *      shape tests/test_ntt.cu:67-100 drives (grid.y = batch) ------------------ */

@@ -131,6 +131,33 @@ def test_cpp_key_text_format(lib):
     assert r.returncode == 0 and "utils ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def test_binary_rns_container_python_and_cpp_agree(lib, tmp_path):
+    """The binary RNS container (residue-domain data as the device holds it + parameter tuple + checksum): Python
+    round trip, damage detection, and the C++ twin (cuHE_Utils::RnsBlob) reads a file written by Python and writes
+    back the identical bytes."""
+    import subprocess
+    import numpy as np
+    from cuhe_b200 import utils
+    a = np.random.default_rng(3).integers(0, 1 << 26, size=(7, 8192), dtype=np.uint32)
+    path = str(tmp_path / "crt.rns")
+    utils.save_rns(path, a, (5, 2, 1, 61, 20, 8191), domain=2, level=0)
+    b, meta = utils.load_rns(path)
+    assert np.array_equal(a, b) and meta["params"] == (5, 2, 1, 61, 20, 8191) and meta["domain"] == 2
+    k = np.random.default_rng(4).integers(0, 1 << 63, size=(2, 3, 1024), dtype=np.uint64)
+    utils.save_rns(str(tmp_path / "ntt.rns"), k, (3, 2, 16, 48, 24, 32767), domain=3, level=0, shard=(1, 2))
+    k2, meta2 = utils.load_rns(str(tmp_path / "ntt.rns"))
+    assert np.array_equal(k, k2) and meta2["shard"] == (1, 2)
+    raw = bytearray(open(path, "rb").read())
+    raw[200] ^= 0x40
+    open(str(tmp_path / "bad.rns"), "wb").write(bytes(raw))
+    with pytest.raises(ValueError):
+        utils.load_rns(str(tmp_path / "bad.rns"))
+    exe = _build_cpp_compat_test("utils_test")
+    r = subprocess.run([exe, path], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "utils ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    assert open(path + ".roundtrip", "rb").read() == open(path, "rb").read()
+
+
 def test_cpp_host_layer_builds_and_exports_the_reference_interface(lib):
     """cuhe_b200/host: the C++ layer with the reference's names (namespace cuHE) compiles with plain
     g++ (no NTL, no nvcc) and a client written against that interface links."""

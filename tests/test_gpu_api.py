@@ -178,3 +178,36 @@ def test_copy_and_errors(ch):
         last.modSwitch()
     with pytest.raises(ch.CuHEError):                  # z2r from the wrong domain
         ca.z2r()
+
+
+def test_operations_on_an_explicit_non_default_stream(ch):
+    """Every operation takes an optional stream (cuhe/CuHE.h:149-208).  With a stream that is NOT torch's current one
+    the buffers are still allocated / zero-filled on the current stream and dropped right after the call, so the
+    mirror has to order the launch after the fill and block like the reference does (cudaStreamSynchronize(st) after
+    every operation, cuhe/CuHE.cu:81-268).  A busy current stream makes a missing dependency visible."""
+    import torch
+    o = get_oracle(SMALL_RELIN)
+    st = torch.cuda.Stream()
+    a, b = rnd(o, 0, 17), rnd(o, 0, 18)
+    want = o.mul_raw_to_crt(o.to_raw(a, 0), o.to_raw(b, 0), 0)
+    ballast = torch.zeros(64 << 20, dtype=torch.uint8, device="cuda")
+    for rep in range(3):
+        for _ in range(20):
+            ballast.add_(1)                            # keep the current stream busy ahead of the allocations
+        ca, cb = ch.CuCtxt(), ch.CuCtxt()
+        ca.setLevel(0, 0, a)
+        cb.setLevel(0, 0, b)
+        ca.x2n(st)
+        cb.x2n(st)
+        cs = ch.CuCtxt()
+        ch.cXor(cs, ca, cb, st)
+        ch.cAnd(ca, ca, cb, st)
+        ca.x2c(st)
+        assert np.array_equal(u32(ca.cRep()), want)
+        cs.x2c(st)
+        ra, rb = o.crt(o.to_raw(a, 0), 0), o.crt(o.to_raw(b, 0), 0)
+        assert np.array_equal(u32(cs.cRep()), o.crt_add(ra, rb))
+        ch.cNot(cs, cs, st)
+        assert np.array_equal(u32(cs.cRep()), o.crt_add_int(o.crt_add(ra, rb), ch.param.modMsg - 1))
+        ca.x2z(st)
+        assert ca.zRep() == o.mul_exact(a, b, 0)

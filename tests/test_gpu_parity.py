@@ -384,6 +384,42 @@ def test_relin(lib, ps):
         e.close()
 
 
+def test_relin_keys_export_import_through_the_binary_container(lib, tmp_path):
+    """cuhe_relin_export_host after cuhe_relin_init equals the oracle's transformed keys (h_ek of
+    cuhe/Relinearization.cu:43-56); written with save_rns, read back and imported into a FRESH context, the key switch
+    gives the same words without any CRT / transform work at start-up."""
+    from cuhe_b200 import utils
+    e = Eng(lib, SMALL_RELIN)
+    e2 = Eng(lib, SMALL_RELIN)
+    try:
+        o = e.orc
+        K0, N, L = o.par.numEvalKey, o.N, o.L(0)
+        rng = random.Random(21)
+        eks = [o.to_raw([rng.randrange(o.moduli[0]) for _ in range(o.n)], 0) for _ in range(K0)]
+        o.init_relin(eks)
+        e.call("cuhe_relin_init", p(e.up(np.stack(eks))), e.st())
+        words = lib.cuhe_relin_key_words(e.h)
+        assert words == L * K0 * N
+        host = np.zeros((L, K0, N), dtype=np.uint64)
+        e.call("cuhe_relin_export_host", host.ctypes.data_as(C.c_void_p), C.c_size_t(words), e.st())
+        assert np.array_equal(host, o.ek)
+        path = str(tmp_path / "ek.rns")
+        utils.save_rns(path, host, SMALL_RELIN, domain=3, level=0)
+        back, meta = utils.load_rns(path)
+        assert meta["params"] == tuple(SMALL_RELIN)
+        back = np.ascontiguousarray(back)
+        e2.call("cuhe_relin_import_host", back.ctypes.data_as(C.c_void_p), C.c_size_t(words), e2.st())
+        _, raw = rand_poly_raw(o, 0, 77)
+        d1, d2 = e.empty((L, N), np.uint64), e2.empty((L, N), np.uint64)
+        e.call("cuhe_relin", p(d1), p(e.up(raw)), 0, e.st())
+        e2.call("cuhe_relin", p(d2), p(e2.up(raw)), 0, e2.st())
+        assert np.array_equal(Eng.dn(d2, np.uint64), o.relin_mac(raw, 0))
+        assert np.array_equal(Eng.dn(d1, np.uint64), Eng.dn(d2, np.uint64))
+    finally:
+        e.close()
+        e2.close()
+
+
 def test_mul_raw_host_end_to_end(eng16):
     e, o = eng16, eng16.orc
     lvl = 0

@@ -62,9 +62,29 @@ def sweep():
     lib.cuhe_ctx_destroy(h)
 
 
+def one():
+    """a few batched forward 64K launch pairs (batch 512, alternating inputs > L2): the workload of bench.py's ncu child"""
+    lib = load_library()
+    par = cuhe_params()
+    check(lib.cuhe_set_parameters(C.byref(par), 24, 2, 16, 24, 24, 32767))
+    h = C.c_void_p()
+    check(lib.cuhe_ctx_create(C.byref(h), C.byref(par), 0, 0, 1))
+    dev = torch.device("cuda", 0)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    N, H, cnt = 65536, 32768, 512
+    src = torch.randint(0, 2**31 - 1, (2, cnt, H), dtype=torch.int32, device=dev)
+    dst = torch.zeros((cnt, N), dtype=torch.int64, device=dev)
+    for i in range(8):
+        check(lib.cuhe_ntt_ext_batch(h, C.c_void_p(dst.data_ptr()), C.c_void_p(src[i % 2].data_ptr()), N, cnt, C.c_longlong(H), st))
+    torch.cuda.synchronize()
+    lib.cuhe_ctx_destroy(h)
+
+
 def main():
     if "--sweep" in sys.argv:
         return sweep()
+    if "--one" in sys.argv:
+        return one()
     lib = load_library()
     par = cuhe_params()
     check(lib.cuhe_set_parameters(C.byref(par), 24, 2, 16, 24, 24, 32767))
