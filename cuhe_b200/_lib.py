@@ -79,6 +79,14 @@ SYMBOLS = {
     "cuhe_mul_crt_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "cuhe_icrt_batch": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "cuhe_icrt_slice_batch": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "cuhe_crt_batch": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "cuhe_ntt_batch": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "cuhe_ntt_mul_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "cuhe_intt_mod_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "cuhe_crt_add_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "cuhe_crt_add_int_batch": (_i, [_vp, _vp, _vp, C.c_uint, _i, _i, _vp]),
+    "cuhe_mod_switch_batch": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "cuhe_relin_batch": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "cuhe_comm_unique_id": (_i, [_vp]),
     "cuhe_ctx_comm_init": (_i, [_vp, _vp]),
     "cuhe_ctx_comm_attach": (_i, [_vp, _vp]),

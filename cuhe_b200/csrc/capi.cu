@@ -160,9 +160,11 @@ static const NttPlan& get_plan(cuhe_ctx* c, int N) {
 
 // ---- transform drivers -------------------------------------------------------
 // Runs pass 1 + pass 2 for `count` transforms through a count*N-word scratch (a.scratch / b.scratch are filled in
-// here).  Measured and dropped in round 2 (profiles/r02_ntt_chunk_sweep.txt): running the two passes over chunks of
-// 16-128 transforms through an L2-sized scratch removes the intermediate's DRAM round trip but is 11-60 % slower
-// (launches of 1-2 waves), and the one-launch cluster variant of round 1 was 17 % slower.
+// here).  Measured and dropped in round 2 (profiles/r02_ntt_chunk_sweep.txt): running the passes over chunks of 16-128
+// transforms through an L2-sized scratch -- one stream, or pass 1 of chunk i+1 concurrent with pass 2 of chunk i on two
+// streams -- cuts the intermediate's DRAM round trip (2.6x -> 1.8x algorithmic) but is 7-60 % slower than one launch
+// pair (launches of 1-2 waves; the kernels are ALU-pipe bound, DRAM at ~35 % of peak); round 1's one-launch cluster
+// variant was 17 % slower.
 static void run_ntt(cuhe_ctx* c, const NttPlan& pl, int mode, int out, Pass1Args a, Pass2Args b, int count,
                     cudaStream_t st) {
     if (count <= 0) return;
@@ -859,7 +861,7 @@ static int crt_add_common(cuhe_ctx* c, uint32_t* sum, const uint32_t* x, const u
         const int rows = c->rows(lvl), H = c->par.crtLen, n = c->par.modLen;
         if (rows == 0) return;
         dim3 grid((n + 255) / 256, rows);
-        crt_add_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(sum, x, y, nx1 ? 0 : H, c->pv(), n, H);
+        crt_add_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(sum, x, y, nx1 ? 0 : H, c->pv(), n, H, rows);
         count_launch();
         CK(cudaGetLastError());
     });
@@ -872,7 +874,7 @@ int cuhe_crt_add_int(cuhe_ctx* c, uint32_t* sum, const uint32_t* x, unsigned a, 
         DeviceGuard dg(c->device);
         const int rows = c->rows(lvl);
         if (rows == 0) return;
-        crt_add_int_kernel<<<(rows + 63) / 64, 64, 0, (cudaStream_t)stream>>>(sum, x, a, c->pv(), rows, c->par.crtLen);
+        crt_add_int_kernel<<<(rows + 63) / 64, 64, 0, (cudaStream_t)stream>>>(sum, x, a, c->pv(), rows, c->par.crtLen, rows);
         count_launch();
         CK(cudaGetLastError());
     });
@@ -887,7 +889,7 @@ int cuhe_mod_switch(cuhe_ctx* c, uint32_t* dst, const uint32_t* src, const uint3
         if (rows == 0) return;
         dim3 grid((n + 127) / 128, rows);
         modswitch_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(dst, src, last_row, c->pv(), rows, c->L(lvl), c->d_invp, n,
-                                                               c->par.crtLen, c->par.modMsg);
+                                                               c->par.crtLen, c->par.modMsg, 0, 0, 0);
         count_launch();
         CK(cudaGetLastError());
     });
@@ -944,42 +946,135 @@ int cuhe_relin_import_host(cuhe_ctx* c, const uint64_t* in_host, size_t words, c
     });
 }
 
+// key switch of `batch` polynomials: raw u32[batch][H][W] -> dst u64[batch][rows][N]     (cuhe/Relinearization.cu:76-88)
+static void relin_impl(cuhe_ctx* c, uint64_t* dst, const uint32_t* raw, int lvl, int batch, cudaStream_t st) {
+    if (!c->d_ek) throw StateError{"cuhe_relin_init has not been called"};
+    const int K = c->par.numEvalKeyAt(lvl), K0 = c->par.numEvalKey, rows = c->rows(lvl), N = c->par.nttLen;
+    if (rows == 0 || batch <= 0) return;
+    REQUIRE((long long)K * batch <= 65535 && batch <= 65535, "batch too large");
+    const NttPlan& pl = get_plan(c, N);
+    // digit transforms, prime independent (nttw, cuhe/Operations.cu:399-403): K per polynomial, one launch pair for all
+    Tmp D(c, (size_t)batch * K * N * 8, st);
+    Pass1Args a{};
+    a.src = raw; a.tw1 = pl.tw1; a.n2 = pl.n2;
+    a.digit_w = c->par.logRelin; a.digit_words = c->par.wordsCoeffAt(lvl); a.digit_first = 0;
+    a.row_mod = K; a.src_stride = (long long)c->par.crtLen * a.digit_words;
+    Pass2Args b{};
+    b.dst = D.as<uint64_t>(); b.tw2 = pl.tw2; b.dst_stride = N; b.row_mod = 1;
+    run_ntt(c, pl, IN_DIGIT, OUT_U64, a, b, K * batch, st);
+    // CUHE_B200_RELIN_RB = 1 (generation 1 kernel), 2 or 4 rows per thread, CUHE_B200_RELIN_UNROLL = 1, 2, 4:
+    // A/B switches, tuning only.  Default: 2 rows, unroll 2 (fastest measured at 44 primes / 66 keys).
+    static const int mac_rb = [] { const char* e = getenv("CUHE_B200_RELIN_RB"); return e ? atoi(e) : 2; }();
+    static const int mac_un = [] { const char* e = getenv("CUHE_B200_RELIN_UNROLL"); return e ? atoi(e) : 2; }();
+    const long long ks = N, ps = (long long)K0 * N;
+    uint64_t* Dp = D.as<uint64_t>();
+    if (mac_rb == 1 && batch == 1) {
+        dim3 grid((N + 255) / 256, rows);
+        relin_mac_kernel<<<grid, 256, 0, st>>>(dst, Dp, c->d_ek, K, ks, ps, 0, 1, N);
+    } else {
+        const int rb = mac_rb == 4 ? 4 : 2;
+        dim3 grid(N / 2 / 128, (rows + rb - 1) / rb, batch);
+#define CUHE_MAC(RB_, UN_) relin_mac_kernel_v2<RB_, UN_><<<grid, 128, 0, st>>>(dst, Dp, c->d_ek, K, ks, ps, 0, 1, N, rows)
+        if (rb == 4) { if (mac_un == 1) CUHE_MAC(4, 1); else if (mac_un == 4) CUHE_MAC(4, 4); else CUHE_MAC(4, 2); }
+        else { if (mac_un == 1) CUHE_MAC(2, 1); else if (mac_un == 4) CUHE_MAC(2, 4); else CUHE_MAC(2, 2); }
+#undef CUHE_MAC
+    }
+    count_launch();
+    CK(cudaGetLastError());
+}
 int cuhe_relin(cuhe_ctx* c, uint64_t* dst, const uint32_t* raw, int lvl, cuhe_stream stream) {
     return guarded([&] {
         check_lvl(c, lvl); REQUIRE(dst && raw, "null pointer");
-        if (!c->d_ek) throw StateError{"cuhe_relin_init has not been called"};
         DeviceGuard dg(c->device);
-        cudaStream_t st = (cudaStream_t)stream;
-        const int K = c->par.numEvalKeyAt(lvl), K0 = c->par.numEvalKey, rows = c->rows(lvl), N = c->par.nttLen;
+        relin_impl(c, dst, raw, lvl, 1, (cudaStream_t)stream);
+    });
+}
+
+// ---- batched forms of the ciphertext operations: `batch` independent ciphertexts of one level per call, layouts
+//      [batch][rows(lvl)][..].  What a circuit layer needs (the 16 S-boxes of a PRINCE layer are independent,
+//      examples/Prince/Prince.cu:191-201: the reference spreads them over OpenMP threads / GPUs, one launch set each).
+static void check_batch(const cuhe_ctx* c, int lvl, int batch) {
+    check_lvl(c, lvl);
+    REQUIRE(batch >= 0 && (long long)batch * std::max(1, c->rows(lvl)) * 2 <= 65535, "batch too large");
+}
+int cuhe_crt_batch(cuhe_ctx* c, uint32_t* dst, const uint32_t* raw, int lvl, int batch, cuhe_stream stream) {
+    return guarded([&] {
+        check_batch(c, lvl, batch); REQUIRE(dst && raw, "null pointer");
+        DeviceGuard dg(c->device);
+        do_crt(c, dst, raw, lvl, batch, (cudaStream_t)stream);
+    });
+}
+int cuhe_ntt_batch(cuhe_ctx* c, uint64_t* dst, const uint32_t* src, int lvl, int batch, cuhe_stream stream) {
+    return guarded([&] {
+        check_batch(c, lvl, batch); REQUIRE(dst && src, "null pointer");
+        DeviceGuard dg(c->device);
+        fwd_ntt(c, c->par.nttLen, dst, src, c->par.crtLen, c->rows(lvl) * batch, nullptr, 1, (cudaStream_t)stream);
+    });
+}
+// n2c of products (isProd): y == NULL: dst = inttMod(x); else dst = inttMod(x .* y)  (cAnd fused into the inverse transform)
+int cuhe_intt_mod_batch(cuhe_ctx* c, uint32_t* dst, const uint64_t* x, const uint64_t* y, int lvl, int batch, cuhe_stream stream) {
+    return guarded([&] {
+        check_batch(c, lvl, batch); REQUIRE(dst && x, "null pointer");
+        DeviceGuard dg(c->device);
+        intt_mod_impl(c, dst, x, y, lvl, batch, (cudaStream_t)stream);
+    });
+}
+int cuhe_ntt_mul_batch(cuhe_ctx* c, uint64_t* z, const uint64_t* x, const uint64_t* y, int lvl, int batch, cuhe_stream stream) {
+    return guarded([&] {
+        check_batch(c, lvl, batch); REQUIRE(z && x && y, "null pointer");
+        DeviceGuard dg(c->device);
+        const int rows = c->rows(lvl) * batch, N = c->par.nttLen;
         if (rows == 0) return;
-        const NttPlan& pl = get_plan(c, N);
-        // digit transforms, prime independent (nttw, cuhe/Operations.cu:399-403)
-        Tmp D(c, (size_t)K * N * 8, st);
-        Pass1Args a{};
-        a.src = raw; a.tw1 = pl.tw1; a.n2 = pl.n2;
-        a.digit_w = c->par.logRelin; a.digit_words = c->par.wordsCoeffAt(lvl); a.digit_first = 0;
-        Pass2Args b{};
-        b.dst = D.as<uint64_t>(); b.tw2 = pl.tw2; b.dst_stride = N; b.row_mod = 1;
-        run_ntt(c, pl, IN_DIGIT, OUT_U64, a, b, K, st);
-        // CUHE_B200_RELIN_RB = 1 (generation 1 kernel), 2 or 4 rows per thread, CUHE_B200_RELIN_UNROLL = 1, 2, 4:
-        // A/B switches, tuning only.  Default: 2 rows, unroll 2 (fastest measured at 44 primes / 66 keys).
-        static const int mac_rb = [] { const char* e = getenv("CUHE_B200_RELIN_RB"); return e ? atoi(e) : 2; }();
-        static const int mac_un = [] { const char* e = getenv("CUHE_B200_RELIN_UNROLL"); return e ? atoi(e) : 2; }();
-        const long long ks = N, ps = (long long)K0 * N;
-        uint64_t* Dp = D.as<uint64_t>();
-        if (mac_rb == 1) {
-            dim3 grid((N + 255) / 256, rows);
-            relin_mac_kernel<<<grid, 256, 0, st>>>(dst, Dp, c->d_ek, K, ks, ps, 0, 1, N);
-        } else {
-            const int rb = mac_rb == 4 ? 4 : 2;
-            dim3 grid(N / 2 / 128, (rows + rb - 1) / rb);
-#define CUHE_MAC(RB_, UN_) relin_mac_kernel_v2<RB_, UN_><<<grid, 128, 0, st>>>(dst, Dp, c->d_ek, K, ks, ps, 0, 1, N, rows)
-            if (rb == 4) { if (mac_un == 1) CUHE_MAC(4, 1); else if (mac_un == 4) CUHE_MAC(4, 4); else CUHE_MAC(4, 2); }
-            else { if (mac_un == 1) CUHE_MAC(2, 1); else if (mac_un == 4) CUHE_MAC(2, 4); else CUHE_MAC(2, 2); }
-#undef CUHE_MAC
-        }
+        dim3 grid(N / 2 / 256, rows);
+        ntt_pointwise_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(z, x, y, N, N);
         count_launch();
         CK(cudaGetLastError());
+    });
+}
+int cuhe_crt_add_batch(cuhe_ctx* c, uint32_t* sum, const uint32_t* x, const uint32_t* y, int lvl, int batch, cuhe_stream stream) {
+    return guarded([&] {
+        check_batch(c, lvl, batch); REQUIRE(sum && x && y, "null pointer");
+        DeviceGuard dg(c->device);
+        const int rows = c->rows(lvl), H = c->par.crtLen, n = c->par.modLen;
+        if (rows * batch == 0) return;
+        dim3 grid((n + 255) / 256, rows * batch);
+        crt_add_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(sum, x, y, H, c->pv(), n, H, rows);
+        count_launch();
+        CK(cudaGetLastError());
+    });
+}
+int cuhe_crt_add_int_batch(cuhe_ctx* c, uint32_t* sum, const uint32_t* x, unsigned a, int lvl, int batch, cuhe_stream stream) {
+    return guarded([&] {
+        check_batch(c, lvl, batch); REQUIRE(sum && x, "null pointer");
+        DeviceGuard dg(c->device);
+        const int rows = c->rows(lvl);
+        if (rows * batch == 0) return;
+        crt_add_int_kernel<<<(rows * batch + 63) / 64, 64, 0, (cudaStream_t)stream>>>(sum, x, a, c->pv(), rows * batch, c->par.crtLen, rows);
+        count_launch();
+        CK(cudaGetLastError());
+    });
+}
+// modSwitch of `batch` ciphertexts: src u32[batch][L(lvl)][H] -> dst u32[batch][L(lvl) - 1][H] (out of place; unsharded contexts)
+int cuhe_mod_switch_batch(cuhe_ctx* c, uint32_t* dst, const uint32_t* src, int lvl, int batch, cuhe_stream stream) {
+    return guarded([&] {
+        check_batch(c, lvl, batch); REQUIRE(dst && src, "null pointer");
+        REQUIRE(lvl + 1 < c->par.depth, "cannot modSwitch on the last level");
+        REQUIRE(c->world == 1, "cuhe_mod_switch_batch needs an unsharded context");
+        DeviceGuard dg(c->device);
+        const int L = c->L(lvl), n = c->par.modLen, H = c->par.crtLen;
+        if (batch == 0) return;
+        dim3 grid((n + 127) / 128, L - 1, batch);
+        modswitch_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(dst, src, src + (size_t)(L - 1) * H, c->pv(), L - 1, L, c->d_invp, n, H,
+                                                               c->par.modMsg, (long long)L * H, (long long)(L - 1) * H, (long long)L * H);
+        count_launch();
+        CK(cudaGetLastError());
+    });
+}
+int cuhe_relin_batch(cuhe_ctx* c, uint64_t* dst, const uint32_t* raw, int lvl, int batch, cuhe_stream stream) {
+    return guarded([&] {
+        check_batch(c, lvl, batch); REQUIRE(dst && raw, "null pointer");
+        DeviceGuard dg(c->device);
+        relin_impl(c, dst, raw, lvl, batch, (cudaStream_t)stream);
     });
 }
 
@@ -1211,42 +1306,94 @@ int cuhe_mul_raw_sharded_batch(cuhe_ctx* c, uint32_t* raw_out, const uint32_t* a
         std::string why;
         NcclApi* api = nccl_api(&why);
         if (!api) throw StateError{why};
-        const long long B = (long long)nb * G;
+        if (!c->have_polymod) throw StateError{"Barrett reduction needs cuhe_ctx_set_poly_modulus_host first"};
         auto rows_of = [&](int j) { return j < L ? (L - j + G - 1) / G : 0; };
         auto pre = [&](int j) { const int qq = L / G, rr = L % G; return j * qq + (j < rr ? j : rr); };
         const int rows_me = rows_of(me);
-        REQUIRE(2 * B * rows_me <= 65535, "batch too large");
-        const size_t seg_me = (size_t)nb * rows_me * H;                       // words per (operand, peer) on the receive side
-        Tmp send(c, (size_t)2 * nb * L * H * 4, st), ca(c, std::max<size_t>(1, (size_t)2 * B * rows_me * H * 4), st);
-        uint32_t* snd[2] = {send.as<uint32_t>(), send.as<uint32_t>() + (size_t)nb * L * H};
-        uint32_t* rcv[2] = {ca.as<uint32_t>(), ca.as<uint32_t>() + (size_t)B * rows_me * H};
-        const uint32_t* raws[2] = {a_raw, b_raw};
-        for (int op = 0; op < 2; op++)
-            for (int j = 0; j < G; j++)
-                do_crt_view(c, snd[op] + (size_t)nb * pre(j) * H, raws[op], PrimeView{c->d_primes, c->d_mus, j, G}, rows_of(j),
-                            lvl, nb, st);
-        NK(api->GroupStart());
-        for (int op = 0; op < 2; op++)
-            for (int j = 0; j < G; j++) {
-                if (rows_of(j) > 0) NK(api->Send(snd[op] + (size_t)nb * pre(j) * H, (size_t)nb * rows_of(j) * H * 4, ncclUint8, j, c->comm, st));
-                if (rows_me > 0) NK(api->Recv(rcv[op] + (size_t)j * seg_me, seg_me * 4, ncclUint8, j, c->comm, st));
+        const int W = c->par.wordsCoeffAt(lvl);
+        // The own batch is processed as up to two chunks on two internal streams; the stages are issued chunk by chunk
+        // in the order  [CRT, exchange 1] x chunks, [transforms] x chunks, [exchange 2, ICRT] x chunks,  so that on every
+        // rank the NCCL operations appear in the same order and the exchange of one chunk runs under the transforms of
+        // the other.  CUHE_B200_SHARD_CHUNKS=1 disables the split (A/B).
+        static const int want_chunks = [] { const char* e = getenv("CUHE_B200_SHARD_CHUNKS"); return e ? atoi(e) : 2; }();
+        const int nchunk = (want_chunks >= 2 && nb >= 8) ? 2 : 1;
+        {
+            std::lock_guard<std::mutex> lk(c->mu);
+            if (!c->s_h2d) {
+                CK(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+                CK(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
+                CK(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
             }
-        NK(api->GroupEnd());
-        const long long cnt = B * rows_me;
-        Tmp prod(c, std::max<size_t>(1, (size_t)cnt * H * 4), st), full(c, (size_t)nb * L * H * 4, st);
-        if (cnt > 0) {
-            if (!c->have_polymod) throw StateError{"Barrett reduction needs cuhe_ctx_set_poly_modulus_host first"};
-            Tmp nab(c, (size_t)2 * cnt * N * 8, st);
-            fwd_ntt(c, N, nab.as<uint64_t>(), ca.as<uint32_t>(), H, (int)(2 * cnt), nullptr, 1, st);
-            intt_mod_impl(c, prod.as<uint32_t>(), nab.as<uint64_t>(), nab.as<uint64_t>() + (size_t)cnt * N, lvl, (int)B, st);
         }
-        NK(api->GroupStart());
-        for (int j = 0; j < G; j++) {
-            if (rows_me > 0) NK(api->Send(prod.as<uint32_t>() + (size_t)j * seg_me, seg_me * 4, ncclUint8, j, c->comm, st));
-            if (rows_of(j) > 0) NK(api->Recv(full.as<uint32_t>() + (size_t)nb * pre(j) * H, (size_t)nb * rows_of(j) * H * 4, ncclUint8, j, c->comm, st));
+        cudaStream_t lane[2] = {c->s_comp, c->s_h2d};
+        struct Ev {
+            cudaEvent_t e = nullptr;
+            Ev() { cudaEventCreateWithFlags(&e, cudaEventDisableTiming); }
+            ~Ev() { if (e) cudaEventDestroy(e); }
+        } ev_start, ev_done[2];
+        CK(cudaEventRecord(ev_start.e, st));
+        struct Chunk {
+            int b0, nbc;
+            std::unique_ptr<Tmp> send, ca, prod, full;
+        } ch[2];
+        for (int k = 0; k < nchunk; k++) {
+            ch[k].b0 = k == 0 ? 0 : nb / 2;
+            ch[k].nbc = nchunk == 1 ? nb : (k == 0 ? nb / 2 : nb - nb / 2);
+            CK(cudaStreamWaitEvent(lane[k], ev_start.e, 0));
         }
-        NK(api->GroupEnd());
-        do_icrt_strided(c, raw_out, full.as<uint32_t>(), lvl, 0, n, nb, H, st, G, nb);
+        // stage 1: CRT of the own operands for every rank's primes, grouped by destination; exchange 1
+        for (int k = 0; k < nchunk; k++) {
+            cudaStream_t s = lane[k];
+            const int nbc = ch[k].nbc;
+            const long long Bc = (long long)nbc * G;
+            REQUIRE(2 * Bc * std::max(1, rows_me) <= 65535, "batch too large");
+            const size_t seg_me = (size_t)nbc * rows_me * H;                  // words per (operand, peer) on the receive side
+            ch[k].send.reset(new Tmp(c, (size_t)2 * nbc * L * H * 4, s));
+            ch[k].ca.reset(new Tmp(c, std::max<size_t>(1, (size_t)2 * Bc * rows_me * H * 4), s));
+            uint32_t* snd[2] = {ch[k].send->as<uint32_t>(), ch[k].send->as<uint32_t>() + (size_t)nbc * L * H};
+            uint32_t* rcv[2] = {ch[k].ca->as<uint32_t>(), ch[k].ca->as<uint32_t>() + (size_t)Bc * rows_me * H};
+            const uint32_t* raws[2] = {a_raw + (size_t)ch[k].b0 * H * W, b_raw + (size_t)ch[k].b0 * H * W};
+            for (int op = 0; op < 2; op++)
+                for (int j = 0; j < G; j++)
+                    do_crt_view(c, snd[op] + (size_t)nbc * pre(j) * H, raws[op], PrimeView{c->d_primes, c->d_mus, j, G}, rows_of(j),
+                                lvl, nbc, s);
+            NK(api->GroupStart());
+            for (int op = 0; op < 2; op++)
+                for (int j = 0; j < G; j++) {
+                    if (rows_of(j) > 0) NK(api->Send(snd[op] + (size_t)nbc * pre(j) * H, (size_t)nbc * rows_of(j) * H * 4, ncclUint8, j, c->comm, s));
+                    if (rows_me > 0) NK(api->Recv(rcv[op] + (size_t)j * seg_me, seg_me * 4, ncclUint8, j, c->comm, s));
+                }
+            NK(api->GroupEnd());
+        }
+        // stage 2: transforms, product, inverse, reduction for the rows of this rank, all nbc*G products of the chunk
+        for (int k = 0; k < nchunk; k++) {
+            cudaStream_t s = lane[k];
+            const long long cnt = (long long)ch[k].nbc * G * rows_me;
+            ch[k].prod.reset(new Tmp(c, std::max<size_t>(1, (size_t)cnt * H * 4), s));
+            if (cnt > 0) {
+                Tmp nab(c, (size_t)2 * cnt * N * 8, s);
+                fwd_ntt(c, N, nab.as<uint64_t>(), ch[k].ca->as<uint32_t>(), H, (int)(2 * cnt), nullptr, 1, s);
+                intt_mod_impl(c, ch[k].prod->as<uint32_t>(), nab.as<uint64_t>(), nab.as<uint64_t>() + (size_t)cnt * N, lvl,
+                              ch[k].nbc * G, s);
+            }
+        }
+        // stage 3: exchange 2 (product rows back to the owners), ICRT of the own products from the grouped buffer
+        for (int k = 0; k < nchunk; k++) {
+            cudaStream_t s = lane[k];
+            const int nbc = ch[k].nbc;
+            const size_t seg_me = (size_t)nbc * rows_me * H;
+            ch[k].full.reset(new Tmp(c, (size_t)nbc * L * H * 4, s));
+            NK(api->GroupStart());
+            for (int j = 0; j < G; j++) {
+                if (rows_me > 0) NK(api->Send(ch[k].prod->as<uint32_t>() + (size_t)j * seg_me, seg_me * 4, ncclUint8, j, c->comm, s));
+                if (rows_of(j) > 0) NK(api->Recv(ch[k].full->as<uint32_t>() + (size_t)nbc * pre(j) * H, (size_t)nbc * rows_of(j) * H * 4, ncclUint8, j, c->comm, s));
+            }
+            NK(api->GroupEnd());
+            do_icrt_strided(c, raw_out + (size_t)ch[k].b0 * H * W, ch[k].full->as<uint32_t>(), lvl, 0, n, nbc, H, s, G, nbc);
+            CK(cudaEventRecord(ev_done[k].e, s));
+            CK(cudaStreamWaitEvent(st, ev_done[k].e, 0));
+        }
+        // the temporaries are released in stream order on their lanes (Tmp destructors)
     });
 }
 #undef NK

@@ -25,7 +25,8 @@ struct Pass1Args {
     long long src2_stride;
     int n2;                    // N / 64
     int digit_w, digit_words;  // IN_DIGIT: window bits, words per coefficient
-    int digit_first;           // IN_DIGIT: transform t extracts window digit_first + t
+    int digit_first;           // IN_DIGIT: transform t extracts window digit_first + t (row_mod = 0), or window
+                               // digit_first + t % row_mod of polynomial t / row_mod at src + (t / row_mod) * src_stride
     // IN_U32_MAP
     int map_len, map_base, map_dir, fold_m, fold_lim;
     const uint32_t* primes;    // fold: p of transform t is primes[prime_base + prime_step*(t % row_mod)]

@@ -77,8 +77,11 @@ __global__ void __launch_bounds__(kP1Threads) ntt96_pass1_kernel(Pass1Args a) {
     int8_t* colh = S1 + tid;
 
     int dg_lo = 0, dg_sh = 0; bool dg_two = false; uint64_t dg_mask = 0;          // cuhe/Base.cu:361-371
+    int dg_poly = 0;                                   // batch of polynomials: row_mod digits each
     if constexpr (MODE == IN_DIGIT) {
-        const int bit = a.digit_w * (a.digit_first + t);
+        int tk = t;
+        if (a.row_mod > 0) { dg_poly = t / a.row_mod; tk = t - dg_poly * a.row_mod; }
+        const int bit = a.digit_w * (a.digit_first + tk);
         dg_lo = bit >> 5; dg_sh = bit & 31;
         dg_two = (dg_lo + 1) < a.digit_words;
         dg_mask = (1ull << a.digit_w) - 1;
@@ -112,7 +115,8 @@ __global__ void __launch_bounds__(kP1Threads) ntt96_pass1_kernel(Pass1Args a) {
                 v[k] = w;
             }
         } else if constexpr (MODE == IN_DIGIT) {
-            const uint32_t* s = (const uint32_t*)a.src + (long long)(i * N2 + j2) * a.digit_words + dg_lo;
+            const uint32_t* s = (const uint32_t*)a.src + (long long)dg_poly * a.src_stride +
+                                (long long)(i * N2 + j2) * a.digit_words + dg_lo;
             const long long step = (long long)8 * N2 * a.digit_words;
 #pragma unroll
             for (int k = 0; k < 4; k++) {

@@ -331,10 +331,14 @@ icrt_kernel_v2(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, con
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 modswitch_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, const uint32_t* __restrict__ last,
-                 PrimeView pv, int rows, int Llevel, const uint32_t* __restrict__ invp, int n, int H, int modmsg) {
+                 PrimeView pv, int rows, int Llevel, const uint32_t* __restrict__ invp, int n, int H, int modmsg,
+                 long long src_poly_stride, long long dst_poly_stride, long long last_poly_stride) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y;
     if (idx >= n || r >= rows) return;
+    src += (long long)blockIdx.z * src_poly_stride;            // batch (0 strides / grid.z = 1: one polynomial)
+    dst += (long long)blockIdx.z * dst_poly_stride;
+    last += (long long)blockIdx.z * last_poly_stride;
     const int j = prime_index(pv, r);
     if (j >= Llevel - 1) return;
     int dirty = (int)last[idx];
@@ -377,19 +381,19 @@ ntt_pointwise_kernel(uint64_t* __restrict__ z, const uint64_t* __restrict__ x, c
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 crt_add_kernel(uint32_t* __restrict__ x, const uint32_t* __restrict__ a, const uint32_t* __restrict__ b,
-               long long b_stride, PrimeView pv, int n, int H) {
+               long long b_stride, PrimeView pv, int n, int H, int row_mod) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = blockIdx.y;
+    const int r = blockIdx.y;                   // row of the batch: residue r % row_mod of polynomial r / row_mod
     if (i >= n) return;
-    const int l = prime_index(pv, r);
+    const int l = prime_index(pv, r % row_mod);
     uint64_t s = (uint64_t)a[(long long)r * H + i] + b[(long long)r * b_stride + i];
     x[(long long)r * H + i] = mod_u64_u32(s, pv.p[l], pv.mu[l]);
 }
 __global__ void crt_add_int_kernel(uint32_t* __restrict__ y, const uint32_t* __restrict__ x, unsigned a,
-                                   PrimeView pv, int rows, int H) {
+                                   PrimeView pv, int rows, int H, int row_mod) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
-    const int l = prime_index(pv, r);
+    const int l = prime_index(pv, r % row_mod);
     const uint32_t p = pv.p[l];
     y[(long long)r * H] = (uint32_t)(((uint64_t)x[(long long)r * H] + (a % p)) % p);
 }
@@ -503,6 +507,8 @@ relin_mac_kernel_v2(uint64_t* __restrict__ dst, const uint64_t* __restrict__ D, 
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
     const int r0 = blockIdx.y * RB;
     if (i >= N) return;
+    dst += (long long)blockIdx.z * rows * N;                   // batch: polynomial z has its own digits and outputs
+    D += (long long)blockIdx.z * K * N;
     const ulonglong2* e[RB];
 #pragma unroll
     for (int j = 0; j < RB; j++) {

@@ -201,6 +201,26 @@ int cuhe_icrt_batch(cuhe_ctx* ctx, uint32_t* raw_out, const uint32_t* crt_all, i
 int cuhe_icrt_slice_batch(cuhe_ctx* ctx, uint32_t* raw_slice_out, const uint32_t* crt_slice, int lvl, int coef_offset,
                           int slice_len, int batch, cuhe_stream stream);
 
+/* ---- batched forms of the ciphertext operations: `batch` independent ciphertexts of ONE level per call, layouts
+ * [batch][rows(lvl)][..] (what a circuit layer needs: the 16 S-boxes of a PRINCE layer are independent,
+ * examples/Prince/Prince.cu:191-201; the reference spreads them over OpenMP threads / GPUs with one launch set each).
+ *   cuhe_crt_batch           r2c x batch       raw u32[batch][rawLen][W] -> u32[batch][rows][crtLen]
+ *   cuhe_ntt_batch           c2n x batch       u32[batch][rows][crtLen] -> u64[batch][rows][nttLen]
+ *   cuhe_ntt_mul_batch       cAnd x batch
+ *   cuhe_intt_mod_batch      n2c of products x batch; with y != NULL the product x .* y is fused into the inverse transform
+ *   cuhe_crt_add_batch / cuhe_crt_add_int_batch     cXor / cNot x batch in the CRT domain
+ *   cuhe_mod_switch_batch    modSwitch x batch, out of place: u32[batch][L][crtLen] -> u32[batch][L-1][crtLen] (unsharded)
+ *   cuhe_relin_batch         relinearization x batch: raw u32[batch][rawLen][W] -> u64[batch][rows][nttLen] */
+int cuhe_crt_batch(cuhe_ctx* ctx, uint32_t* dst, const uint32_t* raw, int lvl, int batch, cuhe_stream stream);
+int cuhe_ntt_batch(cuhe_ctx* ctx, uint64_t* dst, const uint32_t* src, int lvl, int batch, cuhe_stream stream);
+int cuhe_ntt_mul_batch(cuhe_ctx* ctx, uint64_t* z, const uint64_t* x, const uint64_t* y, int lvl, int batch, cuhe_stream stream);
+int cuhe_intt_mod_batch(cuhe_ctx* ctx, uint32_t* dst_crt, const uint64_t* x, const uint64_t* y, int lvl, int batch,
+                        cuhe_stream stream);
+int cuhe_crt_add_batch(cuhe_ctx* ctx, uint32_t* sum, const uint32_t* x, const uint32_t* y, int lvl, int batch, cuhe_stream stream);
+int cuhe_crt_add_int_batch(cuhe_ctx* ctx, uint32_t* sum, const uint32_t* x, unsigned a, int lvl, int batch, cuhe_stream stream);
+int cuhe_mod_switch_batch(cuhe_ctx* ctx, uint32_t* dst, const uint32_t* src, int lvl, int batch, cuhe_stream stream);
+int cuhe_relin_batch(cuhe_ctx* ctx, uint64_t* dst, const uint32_t* raw, int lvl, int batch, cuhe_stream stream);
+
 /* ---- residue-sharded products over the GPUs of one box, exchange inside the library.
  * No reference counterpart: the reference keeps whole ciphertexts per device (one OpenMP thread per GPU,
  * examples/Prince/Prince.cu:194-201; cudaMemcpyPeer in moveTo/copyTo, cuhe/CuHE.cu:217-256).  Here a context

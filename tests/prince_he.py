@@ -389,14 +389,87 @@ class DeviceHomOps(HomOps):
         return t.zRep()
 
 
+class BatchedHomOps(DeviceHomOps):
+    """Device-resident evaluation with the 16 S-boxes of a layer evaluated TOGETHER: bit j of every nibble goes into one
+    cuhe_b200.circuit.CtxtBatch of 16 ciphertexts, and the S-box schedule of the reference (which products are
+    relinearised, where modSwitch happens, Prince.cu:204-322) runs once per layer on batches -- one launch set per
+    operation for all 16 S-boxes instead of 16 launch sets (the reference spreads them over OpenMP threads / GPUs,
+    Prince.cu:191-201).  Same operations on the same data, hence the same ciphertext words as DeviceHomOps."""
+
+    def __init__(self, ch, dhs):
+        super().__init__(ch, dhs)
+        from cuhe_b200.circuit import BatchOps
+        self.bops = BatchOps(0)
+
+    def sbox_layer(self, state, inverse):
+        B, lvl = self.bops, self.level
+        anf = ANF_INV if inverse else ANF_FWD
+        xs = [B.stack([self._at_level(state[4 * i + j], lvl) for i in range(16)]) for j in range(4)]
+        outs = self._sbox16(xs, anf)
+        per_bit = [B.unstack(o) for o in outs]
+        self.level += 2
+        self._views = {k: v for k, v in self._views.items() if k[1] >= self.level}
+        self.counts["sbox"] += 16
+        self.counts.update({k: B.counts[k] for k in ("cAnd", "relin", "modSwitch")})
+        return [per_bit[j][i] for i in range(16) for j in range(4)]
+
+    def _sbox16(self, xs, anf):
+        B = self.bops
+        xn = [B.to_ntt(x.clone()) for x in xs]                         # x2n of the four inputs
+        pairs = {}
+        for i in range(4):
+            for j in range(i + 1, 4):
+                pairs[(i, j)] = B.band(xn[i], xn[j])                   # cAnd; n2c happens inside relin / modSwitch
+        for key in ((0, 1), (2, 3)):                                    # only ab and cd are multiplied again
+            B.relin_(pairs[key])
+        for c in list(pairs.values()) + xs:
+            B.mod_switch_(c)
+        outs = []
+        for monos in anf:                                               # degree <= 2 part, one level down
+            acc = None
+            for mono in monos:
+                if len(mono) not in (1, 2):
+                    continue
+                term = xs[mono[0]] if len(mono) == 1 else pairs[mono]
+                acc = term.clone() if acc is None else B.bxor_(acc, term)
+            if () in monos:
+                B.bnot_(acc)
+            outs.append(acc)
+        xn1 = [B.to_ntt(x.clone()) for x in xs]                         # cubic terms: abd, acd, bcd, abc
+        pn = {k: B.to_ntt(pairs[k].clone()) for k in ((0, 1), (2, 3))}
+        triples = {}
+        for mono, (pk, single) in {(0, 1, 3): ((0, 1), 3), (0, 2, 3): ((2, 3), 0),
+                                   (1, 2, 3): ((2, 3), 1), (0, 1, 2): ((0, 1), 2)}.items():
+            triples[mono] = B.band(pn[pk], xn1[single])
+        for acc, monos in zip(outs, anf):
+            for mono in monos:
+                if len(mono) == 3:
+                    B.bxor_(acc, triples[mono])
+        for acc in outs:
+            B.relin_(acc)
+            B.mod_switch_(acc)
+        return outs
+
+
 def hom_prince(ch, dhs, msg_bits, k0_bits, k1_bits, check_rounds=(), log=None, resident=False):
     """Encrypt the 192 input bits at level 0 (Prince.cu:68-81), evaluate, decrypt at the last level
     (Prince.cu:91-94).  Returns (decrypted 64 bits, HomOps)."""
-    ops = DeviceHomOps(ch, dhs) if resident else HomOps(ch, dhs)
+    import time as _time
+
+    def _sync():
+        try:
+            import torch
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
+        except Exception:                               # the oracle engine has no device
+            pass
+    ops = (BatchedHomOps(ch, dhs) if resident == "batched" else DeviceHomOps(ch, dhs)) if resident else HomOps(ch, dhs)
+    t0 = _time.time()
     enc = lambda b: ops.upload(dhs.encrypt([b], 0))
     msg = [enc(b) for b in msg_bits]
     k0 = [enc(b) for b in k0_bits]
     k1 = [enc(b) for b in k1_bits]
+    ops.seconds = {"encrypt_192_bits_host": _time.time() - t0, "round_checks": 0.0}
     want = kat_round_states() if check_rounds else {}
     got_rounds = {}
 
@@ -404,13 +477,21 @@ def hom_prince(ch, dhs, msg_bits, k0_bits, k1_bits, check_rounds=(), log=None, r
         if log:
             log(f"round {r}: S-box layer done, level {ops.level}")
         if r in check_rounds:
+            _sync()                                     # queued device work belongs to the evaluation, not to the check
+            tc = _time.time()
             bits = [dhs.decrypt(ops.to_zzx(x), ops.level)[0] for x in s]
             got_rounds[r] = bits
+            ops.seconds["round_checks"] += _time.time() - tc
             if log:
                 log(f"round {r}: {''.join(map(str, bits))}")
 
+    t1 = _time.time()
     out = prince_eval(ops, msg, k0, k1, on_round=on_round)
+    _sync()
+    ops.seconds["evaluate"] = _time.time() - t1 - ops.seconds["round_checks"]
+    t2 = _time.time()
     last = dhs.par.depth - 1
     bits = [dhs.decrypt(ops.to_zzx(x), last)[0] for x in out]
+    ops.seconds["decrypt_64_bits_host"] = _time.time() - t2
     ops.round_bits, ops.round_want = got_rounds, {r: want[r] for r in got_rounds}
     return bits, ops

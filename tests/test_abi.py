@@ -273,3 +273,13 @@ def test_lazy_96bit_arithmetic_on_the_host():
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "tests", "cpp", "l96_host_test.cpp")])
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "0 failures, 0 window overflows" in r.stdout, r.stdout + r.stderr
+
+
+def test_reference_include_tree_parses():
+    """compat/cuhe/{CuHE,Parameters,Utils,DeviceManager,Debug}.h: the include tree the reference's unchanged examples
+    resolve `../../cuhe/CuHE.h` against (compat/Makefile builds examples/DHS and examples/Prince from it when NTL is
+    installed); here: a caller written like examples/DHS/DHS.cu:34-55,218 parses against it without NTL."""
+    import subprocess
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "compat"), "-s", "check", f"BUILD={os.path.join('/tmp', 'cuhe_b200_examples_test')}"],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "include tree ok" in r.stdout, r.stdout + r.stderr
