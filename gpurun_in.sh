@@ -1,3 +1,10 @@
 set -x
-python -m pytest tests -x -q -m gpu 2>&1 | tail -5
-cat gpurun_out/prince_kat_timings.jsonl
+python -m pytest tests/test_gpu_multi.py -x -q -m gpu 2>&1 | tail -3
+for ch in 2 1; do
+CUHE_B200_SHARD_CHUNKS=$ch python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_n2_ch$ch.json 2> gpurun_out/bench_n2.err; tail -c 600 gpurun_out/bench_n2.err
+python - <<PY
+import json
+d=json.loads(open('gpurun_out/bench_n2_ch$ch.json').read().strip().splitlines()[-1])
+print("chunks $ch:", {k:d.get(k) for k in ("value","ms_per_step","verified","ntt_64k_per_s")}, "e2e", d["e2e"]["value"], "c5", d["config5"])
+PY
+done
