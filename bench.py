@@ -237,7 +237,7 @@ def measure_ntt_traffic():
         return None, "ncu not found"
     log = os.path.join("/tmp", f"cuhe_b200_ncu_{os.getpid()}.csv")
     cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "--cache-control", "none",
-           "-k", "regex:ntt96_pass", "-s", "8", "-c", "4", "--csv", "--log-file", log,
+           "-k", "regex:ntt4_pass", "-s", "8", "-c", "4", "--csv", "--log-file", log,
            sys.executable, os.path.join(ROOT, "tools", "ntt_bench.py"), "--one"]
     try:
         subprocess.run(cmd, capture_output=True, text=True, timeout=240)
@@ -435,7 +435,7 @@ def run_ours(args):
                 traffic, traffic_src = t["dram_bytes_per_launch_pair"], "committed capture " + t["source"] + " (live measurement: " + traffic_src + ")"
             except Exception:
                 pass
-        roof = {"kernel": "ntt96_pass1_kernel<1024, EXT_U32> + ntt96_pass2_kernel<16, 4, U64> (one batched forward 64K NTT, per GPU)",
+        roof = {"kernel": "ntt4_pass1_kernel<1024, EXT_U32> + ntt4_pass2_kernel<16, U64> (one batched forward 64K NTT, per GPU)",
                 "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
                 "peak_source": pk_src + " (burst copy bandwidth)", "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": NTT_BYTES_64K * cnt, "launch_ms": kms, "batch": cnt,

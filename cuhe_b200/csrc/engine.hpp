@@ -6,7 +6,7 @@
 
 namespace cuhe_b200 {
 
-// ---- NTT pass 1 / pass 2 arguments (kernels in ntt96.cuh) ------------------
+// ---- NTT pass 1 / pass 2 arguments (kernels in ntt4.cuh) ------------------
 enum Pass1In {
     IN_EXT_U32 = 0,     // u32[N/2] zero-padded input                        (ntt_1_*_ext)
     IN_DIGIT = 1,       // w-bit window of multi-word raw coefficients        (ntt_1_*_ext_block)

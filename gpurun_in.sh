@@ -1,10 +1,11 @@
 set -x
-python -m pytest tests/test_gpu_multi.py -x -q -m gpu 2>&1 | tail -3
-for ch in 2 1; do
-CUHE_B200_SHARD_CHUNKS=$ch python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_n2_ch$ch.json 2> gpurun_out/bench_n2.err; tail -c 600 gpurun_out/bench_n2.err
+python -m pytest tests -x -q -m gpu 2>&1 | tail -4
+python tools/ntt_bench.py | cut -c1-420
+python bench.py --steps 20 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -c 300 gpurun_out/bench_n1.err
 python - <<PY
 import json
-d=json.loads(open('gpurun_out/bench_n2_ch$ch.json').read().strip().splitlines()[-1])
-print("chunks $ch:", {k:d.get(k) for k in ("value","ms_per_step","verified","ntt_64k_per_s")}, "e2e", d["e2e"]["value"], "c5", d["config5"])
+d=json.loads(open('gpurun_out/bench_n1.json').read().strip().splitlines()[-1])
+print({k:d.get(k) for k in ("value","ms_per_step","ntt_64k_per_s","gpu_launches")}, "e2e", d["e2e"]["value"], "roof", d["roofline"])
 PY
-done
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_r02b.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-c5 > /dev/null 2>&1
+ncu --set full --import-source on --clock-control none -k regex:ntt4_pass -s 6 -c 2 -o gpurun_out/r02_gen4b_ntt python tools/ntt_bench.py --one > /dev/null 2>&1

@@ -275,6 +275,19 @@ def test_lazy_96bit_arithmetic_on_the_host():
     assert r.returncode == 0 and "0 failures, 0 window overflows" in r.stdout, r.stdout + r.stderr
 
 
+def test_ntt_pass_kernels_emulated_on_the_host():
+    """cuhe_b200/csrc/ntt4.cuh: the phase bodies of the two NTT pass kernels are __host__ __device__; every CTA is run
+    thread by thread, phase by phase on the CPU (exact 128-bit intermediates, 96-bit window enforced) for N = 16384,
+    32768, 65536: forward outputs against the definition X[k] = sum x[j] w^(jk), inverse + %p round trip, the fused
+    pointwise product against a convolution, the table epilogue (tests/cpp/ntt4_host_test.cpp)."""
+    import subprocess
+    exe = os.path.join(ROOT, "tests", "_ntt4_host_test")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I", "/usr/local/cuda/include", "-o", exe,
+                           os.path.join(ROOT, "tests", "cpp", "ntt4_host_test.cpp")])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "0 failures, 0 window overflows" in r.stdout, r.stdout + r.stderr
+
+
 def test_reference_include_tree_parses():
     """compat/cuhe/{CuHE,Parameters,Utils,DeviceManager,Debug}.h: the include tree the reference's unchanged examples
     resolve `../../cuhe/CuHE.h` against (compat/Makefile builds examples/DHS and examples/Prince from it when NTL is
