@@ -1211,13 +1211,22 @@ int cuhe_mul_raw_host_batch(cuhe_ctx* c, uint32_t* out_h, const uint32_t* a_h, c
         CK(cudaEventRecord(ready, c->s_comp));               // buffers exist
         CK(cudaStreamWaitEvent(c->s_h2d, ready, 0));
         CK(cudaMemsetAsync(ro.p, 0, (size_t)batch * poly_w * 4, c->s_comp));
+        const size_t pitch = poly_w * 4, live = (size_t)c->par.modLen * W * 4;   // bytes per polynomial / bytes that are not zero
+        if (live < pitch) {
+            CK(cudaMemset2DAsync((char*)ra.p + live, pitch, 0, pitch - live, batch, c->s_comp));
+            CK(cudaMemset2DAsync((char*)rb.p + live, pitch, 0, pitch - live, batch, c->s_comp));
+            CK(cudaEventRecord(ready, c->s_comp));
+            CK(cudaStreamWaitEvent(c->s_h2d, ready, 0));
+        }
         std::vector<cudaEvent_t> ev(2 * nchunk);
         for (auto& e : ev) e = evs.make();
         for (int i = 0, b0 = 0; i < nchunk; b0 += sizes[i], i++) {
             const int nb = sizes[i];
-            const size_t off = (size_t)b0 * poly_w, bytes = (size_t)nb * poly_w * 4;
-            CK(cudaMemcpyAsync(ra.as<uint32_t>() + off, a_h + off, bytes, cudaMemcpyHostToDevice, c->s_h2d));
-            CK(cudaMemcpyAsync(rb.as<uint32_t>() + off, b_h + off, bytes, cudaMemcpyHostToDevice, c->s_h2d));
+            const size_t off = (size_t)b0 * poly_w;
+            // only the modLen rows a ring element has cross PCIe (the rest of a RAW polynomial is zero by
+            // definition and is zeroed on the device): 2-D copies of nb x (modLen*W words) with pitch H*W words
+            CK(cudaMemcpy2DAsync(ra.as<uint32_t>() + off, pitch, a_h + off, pitch, live, nb, cudaMemcpyHostToDevice, c->s_h2d));
+            CK(cudaMemcpy2DAsync(rb.as<uint32_t>() + off, pitch, b_h + off, pitch, live, nb, cudaMemcpyHostToDevice, c->s_h2d));
             CK(cudaEventRecord(ev[2 * i], c->s_h2d));
             CK(cudaStreamWaitEvent(c->s_comp, ev[2 * i], 0));
             uint32_t* cci = cc.as<uint32_t>() + (size_t)b0 * L * H;
@@ -1225,8 +1234,11 @@ int cuhe_mul_raw_host_batch(cuhe_ctx* c, uint32_t* out_h, const uint32_t* a_h, c
             do_icrt(c, ro.as<uint32_t>() + off, cci, lvl, 0, c->par.modLen, nb, c->s_comp);   // c2r (cuhe/CuHE.cu:366-382)
             CK(cudaEventRecord(ev[2 * i + 1], c->s_comp));
             CK(cudaStreamWaitEvent(c->s_d2h, ev[2 * i + 1], 0));
-            CK(cudaMemcpyAsync(out_h + off, ro.as<uint32_t>() + off, bytes, cudaMemcpyDeviceToHost, c->s_d2h));
+            CK(cudaMemcpy2DAsync(out_h + off, pitch, ro.as<uint32_t>() + off, pitch, live, nb, cudaMemcpyDeviceToHost, c->s_d2h));
         }
+        // rows modLen..crtLen of every result are zero: written by the host while the pipeline drains
+        if (live < pitch)
+            for (int b = 0; b < batch; b++) memset((char*)(out_h + (size_t)b * poly_w) + live, 0, pitch - live);
         CK(cudaStreamSynchronize(c->s_d2h));
         CK(cudaStreamSynchronize(c->s_comp));
     });

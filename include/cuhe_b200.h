@@ -176,6 +176,9 @@ int cuhe_intt_batch(cuhe_ctx* ctx, uint64_t* dst, const uint64_t* src, int nttLe
 /* ---- end to end from host buffers: the device part of mulZZX
  *      (cuhe/CuHE.cu:259-268: z2r, r2c, c2n x2, cAnd, n2c, c2r, r2z) ------------
  * a,b,out: RAW u32[crtLen][words(lvl)] in host memory (pinned for best speed).
+ * Operands are ring elements: coefficients modLen..crtLen-1 are zero by definition (what z2r produces,
+ * cuhe/CuHE.cu:317-331) and are NOT read -- only modLen rows per polynomial cross PCIe in either direction;
+ * the same rows of `out` are written as zero.
  * Single-shard contexts only.  Synchronous on return. */
 int cuhe_mul_raw_host(cuhe_ctx* ctx, uint32_t* out_raw_host, const uint32_t* a_raw_host,
                       const uint32_t* b_raw_host, int lvl, cuhe_stream stream);
