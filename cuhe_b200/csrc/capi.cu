@@ -356,6 +356,34 @@ static void launch_icrt(uint32_t* dst, const uint32_t* src, cuhe_ctx* c, const I
     }
     count_launch();
 }
+// generation 3 (lazy column sums, padded word count a template constant): exact M_l rows, W <= 64, primes below 2^26
+template <int W4>
+static void launch_icrt_v3_w(uint32_t* dst, const uint32_t* src, cuhe_ctx* c, const IcrtDev& ic, int b, int e, int batch,
+                             int Hs, cudaStream_t st, int grp_G, int grp_nb) {
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !done[dev]) {
+        CK(cudaFuncSetAttribute(icrt_kernel_v3<W4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        done[dev] = true;
+    }
+    const int cnt = e - b;
+    dim3 grid((cnt + 127) / 128, batch);
+    const size_t smem = (size_t)((ic.L * W4 + W4 + 4 + 2 * ic.L + 1) & ~1) * 4 + (size_t)ic.L * 8;
+    icrt_kernel_v3<W4><<<grid, 128, smem, st>>>(dst, src, c->d_primes, c->d_mus, ic.M, ic.mi, ic.bi, ic.m_top, ic.L, ic.W, ic.Wp,
+                                                b, e, Hs, grp_G, grp_nb);
+    count_launch();
+}
+static bool launch_icrt_v3(uint32_t* dst, const uint32_t* src, cuhe_ctx* c, const IcrtDev& ic, int b, int e, int batch, int Hs,
+                           cudaStream_t st, int grp_G, int grp_nb) {
+    if (ic.truncated || ic.W > 64 || ic.W < 2 || ic.Wp > ic.W) return false;   // primes < 2^26: context creation
+    switch ((ic.W + 3) / 4) {
+#define ICRT3(q) case q: launch_icrt_v3_w<4 * q>(dst, src, c, ic, b, e, batch, Hs, st, grp_G, grp_nb); return true;
+        ICRT3(1) ICRT3(2) ICRT3(3) ICRT3(4) ICRT3(5) ICRT3(6) ICRT3(7) ICRT3(8) ICRT3(9) ICRT3(10) ICRT3(11) ICRT3(12) ICRT3(13) ICRT3(14) ICRT3(15) ICRT3(16)
+#undef ICRT3
+    }
+    return false;
+}
 template <int WMAX>
 static void launch_crt(cuhe_ctx* c, uint32_t* dst, const uint32_t* raw, PrimeView pv, int rows, int W, int batch,
                        cudaStream_t st) {
@@ -379,6 +407,7 @@ static void do_icrt_strided(cuhe_ctx* c, uint32_t* raw_out, const uint32_t* crt_
                             int Hs, cudaStream_t st, int grp_G = 0, int grp_nb = 0) {
     if (b >= e || batch <= 0) return;
     const IcrtDev& ic = c->icrt[lvl];
+    if (launch_icrt_v3(raw_out, crt_all, c, ic, b, e, batch, Hs, st, grp_G, grp_nb)) { CK(cudaGetLastError()); return; }
     if (ic.W <= 8) launch_icrt<8>(raw_out, crt_all, c, ic, b, e, batch, Hs, st, grp_G, grp_nb);
     else if (ic.W <= 20) launch_icrt<20>(raw_out, crt_all, c, ic, b, e, batch, Hs, st, grp_G, grp_nb);
     else if (ic.W <= 36) launch_icrt<36>(raw_out, crt_all, c, ic, b, e, batch, Hs, st, grp_G, grp_nb);
@@ -392,11 +421,37 @@ static void do_icrt(cuhe_ctx* c, uint32_t* raw_out, const uint32_t* crt_all, int
     if (e > c->par.modLen) e = c->par.modLen;     // the reference writes idx < modLen only
     do_icrt_strided(c, raw_out, crt_all, lvl, b, e, batch, c->par.crtLen, st);
 }
+// generation 3 (padded word count a template constant): W <= 64 and every prime below 2^26
+template <int W4>
+static void launch_crt_v3_w(cuhe_ctx* c, uint32_t* dst, const uint32_t* raw, PrimeView pv, int rows, int W, int batch, cudaStream_t st) {
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !done[dev]) {
+        CK(cudaFuncSetAttribute(crt_kernel_v3<W4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        done[dev] = true;
+    }
+    const int H = c->par.crtLen;
+    const size_t smem = (size_t)(((rows * W4 + rows + 1) & ~1)) * 4 + (size_t)rows * 8;
+    dim3 grid((H + 127) / 128, batch);
+    crt_kernel_v3<W4><<<grid, 128, smem, st>>>(dst, raw, pv, rows, c->d_pow32, c->pow_stride, W, c->par.modLen, H);
+    count_launch();
+}
+static bool launch_crt_v3(cuhe_ctx* c, uint32_t* dst, const uint32_t* raw, PrimeView pv, int rows, int W, int batch, cudaStream_t st) {
+    if (W > 64) return false;           // (every CRT prime is below 2^26, checked at context creation: 16 products per 64-bit sum)
+    switch ((W + 3) / 4) {
+#define CRT3(q) case q: launch_crt_v3_w<4 * q>(c, dst, raw, pv, rows, W, batch, st); return true;
+        CRT3(1) CRT3(2) CRT3(3) CRT3(4) CRT3(5) CRT3(6) CRT3(7) CRT3(8) CRT3(9) CRT3(10) CRT3(11) CRT3(12) CRT3(13) CRT3(14) CRT3(15) CRT3(16)
+#undef CRT3
+    }
+    return false;
+}
 // CRT of `batch` polynomials for the residues of `pv`: raw u32[batch][H][W] -> dst u32[batch][rows][H]
 static void do_crt_view(cuhe_ctx* c, uint32_t* dst, const uint32_t* raw, PrimeView pv, int rows, int lvl, int batch,
                         cudaStream_t st) {
     const int W = c->par.wordsCoeffAt(lvl);
     if (rows == 0 || batch <= 0) return;
+    if (launch_crt_v3(c, dst, raw, pv, rows, W, batch, st)) { CK(cudaGetLastError()); return; }
     if (W <= 8) launch_crt<8>(c, dst, raw, pv, rows, W, batch, st);
     else if (W <= 20) launch_crt<20>(c, dst, raw, pv, rows, W, batch, st);
     else if (W <= 36) launch_crt<36>(c, dst, raw, pv, rows, W, batch, st);

@@ -173,6 +173,72 @@ crt_kernel_v2(uint32_t* __restrict__ dst, const uint32_t* __restrict__ raw, Prim
 }
 
 // ---------------------------------------------------------------------------
+// CRT, generation 3: the (padded) word count is a template constant, so the inner loop is straight-line code --
+// generation 2 kept a runtime W inside a WMAX bucket, which cost a branch per four multiply-adds and an integer
+// division per staged word (100 M warp instructions for 32 polynomials at config 2, a third of them multiply-adds).
+// Here: W4 = W rounded up to a multiple of 4 is the template parameter (table rows zero-padded to it), a thread
+// reads the W words of its coefficient straight from global memory (64-bit loads when W is even; no staging, no
+// division), the residue loop is unrolled twice (four independent 64-bit sums in flight), p and floor(2^64/p) sit in
+// shared memory beside the 2^(32k) mod p table.  Needs p < 2^26 (16 products of < 2^58 per sum); the launcher falls
+// back to generation 2 otherwise.
+// ---------------------------------------------------------------------------
+template <int W4>
+__global__ void __launch_bounds__(128)
+crt_kernel_v3(uint32_t* __restrict__ dst, const uint32_t* __restrict__ raw, PrimeView pv, int rows,
+              const uint32_t* __restrict__ pow32, int pow_stride, int W, int n, int H) {   // dst: [batch][rows][H]
+    static_assert(W4 % 4 == 0 && W4 >= 4, "padded word count must be a multiple of 4");
+    extern __shared__ uint32_t sh[];          // [rows][W4] powers, [rows] p, [rows] mu (u64, 8-byte aligned)
+    uint32_t* spw = sh;
+    uint32_t* sp = sh + rows * W4;
+    uint64_t* smu = reinterpret_cast<uint64_t*>(sh + ((rows * W4 + rows + 1) & ~1));
+    for (int e = threadIdx.x; e < rows * W4; e += 128) {
+        const int r = e / W4, k = e - r * W4;                     // W4 is a constant: multiply-shift
+        spw[e] = k < W ? pow32[(long long)prime_index(pv, r) * pow_stride + k] : 0u;
+    }
+    for (int r = threadIdx.x; r < rows; r += 128) { const int l = prime_index(pv, r); sp[r] = pv.p[l]; smu[r] = pv.mu[l]; }
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    dst += (long long)blockIdx.y * rows * H;
+    uint32_t c[W4];
+    {   // every thread loads (index clamped into the polynomial; words >= W are zero): leaving c[] undefined for
+        // the threads past n makes the compiler carry every word as a 64-bit value, 3 instructions per multiply-add
+        const uint32_t* src = raw + ((long long)blockIdx.y * H + min(i, H - 1)) * W;
+        if ((W & 1) == 0) {
+#pragma unroll
+            for (int k = 0; k < W4; k += 2) {
+                uint2 q = make_uint2(0u, 0u);
+                if (k < W) q = __ldg(reinterpret_cast<const uint2*>(src + k));
+                c[k] = q.x; c[k + 1] = q.y;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < W4; k++) c[k] = k < W ? __ldg(src + k) : 0u;
+        }
+    }
+    __syncthreads();
+    if (i >= n) {
+        if (i < H) for (int r = 0; r < rows; r++) dst[(long long)r * H + i] = 0;
+        return;
+    }
+#pragma unroll 2
+    for (int r = 0; r < rows; r++) {
+        const uint32_t* pw = spw + r * W4;
+        const uint32_t p = sp[r];
+        const uint64_t mu = smu[r];
+        uint64_t a0 = 0, a1 = 0; uint32_t part = 0;
+#pragma unroll
+        for (int k = 0; k < W4; k += 4) {
+            const uint4 q = *reinterpret_cast<const uint4*>(pw + k);      // 128-bit broadcast load
+            a0 += (uint64_t)c[k] * q.x; a1 += (uint64_t)c[k + 1] * q.y;
+            a0 += (uint64_t)c[k + 2] * q.z; a1 += (uint64_t)c[k + 3] * q.w;
+            if ((k + 4) % 32 == 0 && k + 4 < W4) {                        // 16 products per sum: fold before the next 16
+                part = mod_u64_u32(a0 + a1 + part, p, mu); a0 = a1 = 0;
+            }
+        }
+        dst[(long long)r * H + i] = mod_u64_u32(a0 + a1 + part, p, mu);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // ICRT, generation 2.  When no M_l was byte-truncated (checked on the host; the
 // reference would silently drop bits, cuhe/Operations.cu:127-128) the reference's
 // "add one term, subtract M once if >= M" loop (cuhe/Base.cu:880-924) returns
@@ -321,6 +387,131 @@ icrt_kernel_v2(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, con
 #pragma unroll
     for (int k = 0; k < WMAX; k++)
         if (k < W) dst[(long long)idx * W + k] = sum[k];
+}
+
+// ---------------------------------------------------------------------------
+// ICRT, generation 3: lazy column sums.  With tt_l < p_l < 2^26 every product tt_l * (word of M_l) is below 2^58, so
+// up to 32 of them fit one 64-bit accumulator per word: the row multiply-accumulate is ONE IMAD.WIDE per word with
+// no carry chain at all, carries are propagated once per 32 residues.  (Generation 2 ran two PTX carry chains whose
+// operands had to be moved into aligned register pairs: 160 instructions per residue, ~60 here.)  The padded word
+// count W4 is a template constant (rows of the M_l table and M itself are zero-padded to it, so the tail words take
+// part in every loop as zeros), the residue of the next prime is loaded while the current one is accumulated,
+// p / floor(2^64/p) / b_l sit in shared memory.  Same single final reduction as generation 2.  Falls back to
+// generation 2 for truncated M_l or primes >= 2^26.
+// ---------------------------------------------------------------------------
+template <int W4>
+__global__ void __launch_bounds__(128)
+icrt_kernel_v3(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, const uint32_t* __restrict__ primes,
+               const uint64_t* __restrict__ mus, const uint32_t* __restrict__ M, const uint32_t* __restrict__ mi,
+               const uint32_t* __restrict__ bi, double m_top, int L, int W, int Wp, int i_begin, int i_end, int H,
+               int grp_G, int grp_nb) {
+    static_assert(W4 % 4 == 0 && W4 >= 4, "padded word count must be a multiple of 4");
+    extern __shared__ uint32_t sh[];          // [L][W4] M_l, [W4 + 4] M, [L] p, [L] b, [L] mu (u64)
+    uint32_t* smi = sh;
+    uint32_t* sM = sh + L * W4;
+    uint32_t* sp = sM + W4 + 4;
+    uint32_t* sb = sp + L;
+    uint64_t* smu = reinterpret_cast<uint64_t*>(sh + ((L * W4 + W4 + 4 + 2 * L + 1) & ~1));
+    for (int e = threadIdx.x; e < L * W4; e += 128) {
+        const int l = e / W4, k = e - l * W4;
+        smi[e] = k < Wp ? mi[(long long)l * Wp + k] : 0u;
+    }
+    for (int e = threadIdx.x; e < W4 + 4; e += 128) sM[e] = e < W ? M[e] : 0u;
+    for (int l = threadIdx.x; l < L; l += 128) { sp[l] = primes[l]; sb[l] = bi[l]; smu[l] = mus[l]; }
+    __syncthreads();
+    const int idx = i_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= i_end) return;
+    const int bat = blockIdx.y;
+    dst += (long long)blockIdx.y * H * W;
+    uint32_t sum[W4 + 4];
+#pragma unroll
+    for (int k = 0; k < W4 + 4; k++) sum[k] = 0;
+    uint64_t acc[W4];
+#pragma unroll
+    for (int k = 0; k < W4; k++) acc[k] = 0;
+    auto flush = [&]() {                       // sum += acc (column sums -> words), acc = 0
+        uint64_t carry = 0;
+#pragma unroll
+        for (int k = 0; k < W4; k++) {
+            const uint64_t lo = (uint64_t)sum[k] + (uint32_t)acc[k] + (uint32_t)carry;
+            sum[k] = (uint32_t)lo;
+            carry = (carry >> 32) + (acc[k] >> 32) + (lo >> 32);
+            acc[k] = 0;
+        }
+#pragma unroll
+        for (int k = W4; k < W4 + 4; k++) {
+            const uint64_t lo = (uint64_t)sum[k] + (uint32_t)carry;
+            sum[k] = (uint32_t)lo;
+            carry = (carry >> 32) + (lo >> 32);
+        }
+    };
+    uint32_t cur = src[icrt_src_row(0, bat, L, H, grp_G, grp_nb) + idx];
+    for (int l0 = 0; l0 < L; l0 += 32) {       // at most 32 products per column sum between two flushes
+        const int l1 = min(l0 + 32, L);
+        for (int l = l0; l < l1; l++) {
+            const uint32_t nxt = (l + 1 < L) ? src[icrt_src_row(l + 1, bat, L, H, grp_G, grp_nb) + idx] : 0u;
+            // (c mod p) * b mod p == (c * b) mod p: one reduction (c < 2^32, b < 2^26)
+            const uint32_t tt = mod_u64_u32((uint64_t)cur * sb[l], sp[l], smu[l]);
+            const uint32_t* m = smi + l * W4;
+#pragma unroll
+            for (int k = 0; k < W4; k += 4) {
+                const uint4 q = *reinterpret_cast<const uint4*>(m + k);   // 128-bit broadcast load
+                acc[k] += (uint64_t)tt * q.x; acc[k + 1] += (uint64_t)tt * q.y;
+                acc[k + 2] += (uint64_t)tt * q.z; acc[k + 3] += (uint64_t)tt * q.w;
+            }
+            cur = nxt;
+        }
+        flush();
+    }
+    // S = sum < L*M.  Quotient estimate from the top three words (scaled by 2^(-32(W-2)) like m_top).
+    double sd = 0.0;
+#pragma unroll
+    for (int k = 0; k < W4 + 1; k++) {
+        if (k == W) sd += (double)sum[k] * 18446744073709551616.0;
+        if (k == W - 1) sd += (double)sum[k] * 4294967296.0;
+        if (k == W - 2) sd += (double)sum[k];
+    }
+    int cq = (int)(sd / m_top) - 1;
+    if (cq < 0) cq = 0;
+    {   // S -= cq * M   (words of M beyond W are zero)
+        uint64_t borrow = 0;
+        const uint32_t q = (uint32_t)cq;
+#pragma unroll
+        for (int k = 0; k < W4 + 1; k++) {
+            const uint64_t sub = (uint64_t)q * sM[k] + borrow;
+            const uint64_t lo = sub & 0xFFFFFFFFull;
+            const uint64_t t = (uint64_t)sum[k] - lo;
+            sum[k] = (uint32_t)t;
+            borrow = (sub >> 32) + ((t >> 63) & 1);
+        }
+    }
+#pragma unroll 1
+    for (int it = 0; it < 4; it++) {          // S in [0, 3M) here; bring it below M
+        bool ge = true, decided = false;
+#pragma unroll
+        for (int k = W4; k >= 0; k--) {
+            if (!decided) {
+                const uint32_t mk = sM[k];
+                if (sum[k] != mk) { ge = sum[k] > mk; decided = true; }
+            }
+        }
+        if (!ge) break;
+        uint32_t borrow = 0;
+#pragma unroll
+        for (int k = 0; k < W4 + 1; k++) {
+            const uint64_t t = (uint64_t)sum[k] - sM[k] - borrow;
+            sum[k] = (uint32_t)t;
+            borrow = (uint32_t)(t >> 63);
+        }
+    }
+    uint32_t* o = dst + (long long)idx * W;
+    if ((W & 1) == 0) {
+#pragma unroll
+        for (int k = 0; k < W4; k += 2) if (k < W) *reinterpret_cast<uint2*>(o + k) = make_uint2(sum[k], sum[k + 1]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < W4; k++) if (k < W) o[k] = sum[k];
+    }
 }
 
 // ---------------------------------------------------------------------------
