@@ -364,14 +364,16 @@ static void launch_icrt_v3_w(uint32_t* dst, const uint32_t* src, cuhe_ctx* c, co
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 64 && !done[dev]) {
-        CK(cudaFuncSetAttribute(icrt_kernel_v3<W4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CK(cudaFuncSetAttribute(icrt_kernel_v3<W4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CK(cudaFuncSetAttribute(icrt_kernel_v3<W4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         done[dev] = true;
     }
     const int cnt = e - b;
     dim3 grid((cnt + 127) / 128, batch);
     const size_t smem = (size_t)((ic.L * W4 + W4 + 4 + 2 * ic.L + 1) & ~1) * 4 + (size_t)ic.L * 8;
-    icrt_kernel_v3<W4><<<grid, 128, smem, st>>>(dst, src, c->d_primes, c->d_mus, ic.M, ic.mi, ic.bi, ic.m_top, ic.L, ic.W, ic.Wp,
-                                                b, e, Hs, grp_G, grp_nb);
+    auto* fn = ic.L <= 32 ? icrt_kernel_v3<W4, false> : icrt_kernel_v3<W4, true>;
+    fn<<<grid, 128, smem, st>>>(dst, src, c->d_primes, c->d_mus, ic.M, ic.mi, ic.bi, ic.m_top, ic.L, ic.W, ic.Wp, b, e, Hs, grp_G,
+                                grp_nb);
     count_launch();
 }
 static bool launch_icrt_v3(uint32_t* dst, const uint32_t* src, cuhe_ctx* c, const IcrtDev& ic, int b, int e, int batch, int Hs,

@@ -34,21 +34,28 @@ __device__ __forceinline__ uint32_t cyc_addm(uint32_t a, uint32_t b, uint32_t p)
 __device__ __forceinline__ uint32_t cyc_subm(uint32_t a, uint32_t b, uint32_t p) { return a >= b ? a - b : a + p - b; }
 
 // buf[0..len) *= (1 - x^d) as a power series truncated at len: c_i = a_i - a_(i-d).  Block-wide, in place.
-__device__ __forceinline__ void cyc_mul(uint32_t* buf, int len, int d, uint32_t p) {
-    if (d >= len) return;
-    uint32_t v[kCycMaxK];
+template <int K>
+__device__ __forceinline__ void cyc_mul_k(uint32_t* buf, int len, int d, uint32_t p) {
+    uint32_t v[K];
 #pragma unroll
-    for (int k = 0; k < kCycMaxK; k++) {
+    for (int k = 0; k < K; k++) {
         const int i = threadIdx.x + k * kCycT;
         if (i < len) v[k] = i >= d ? cyc_subm(buf[i], buf[i - d], p) : buf[i];
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < kCycMaxK; k++) {
+    for (int k = 0; k < K; k++) {
         const int i = threadIdx.x + k * kCycT;
         if (i < len) buf[i] = v[k];
     }
     __syncthreads();
+}
+__device__ __forceinline__ void cyc_mul(uint32_t* buf, int len, int d, uint32_t p) {
+    if (d >= len) return;
+    // the series these passes run over are short (m - n + small factors: ~6000 words at config 2): do not
+    // issue 32 predicated-off iterations for 6 live ones
+    if (len <= 8 * kCycT) cyc_mul_k<8>(buf, len, d, p);
+    else cyc_mul_k<kCycMaxK>(buf, len, d, p);
 }
 // buf[0..len) /= (1 - x^d) as a power series: b_i = a_i + b_(i-d), a prefix sum down every residue class mod d.
 // d >= kCycT: one class per thread (classes are short); d < kCycT: G = kCycT/d threads share a class, each scans a
@@ -104,13 +111,19 @@ cyclo_reduce_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ hol
     const int r = blockIdx.x, tid = threadIdx.x;
     const uint32_t p = pv.p[pv.base + pv.step * (r % row_mod)];
     const uint32_t* f = hold + (long long)r * N;
-    auto fold = [&](int i) {                        // f'[i] = f[i] + f[i + m]   (f mod x^m - 1)
-        uint32_t v = f[i];
-        if (i + m < N) v = cyc_addm(v, f[i + m], p);
-        return v;
-    };
+    // f'[i] = f[i] + f[i + m]   (f mod x^m - 1), folded where f is read
     // ---- quotient: rev(q) = rev(top k1 of f') * prod_D (1 - x^d) / prod_B (1 - x^d)  mod x^k1
-    for (int j = tid; j < k1; j += kCycT) q[j] = fold(m - 1 - j);
+    for (int j0 = tid; j0 < k1; j0 += 4 * kCycT) {
+        uint32_t a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int j = j0 + u * kCycT, i = m - 1 - j;
+            a[u] = j < k1 ? f[i] : 0u;
+            b[u] = (j < k1 && i + m < N) ? f[i + m] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const int j = j0 + u * kCycT; if (j < k1) q[j] = cyc_addm(a[u], b[u], p); }
+    }
     __syncthreads();
     for (int e = 0; e < plan.nD; e++) cyc_mul(q, k1, plan.D[e], p);
     for (int e = 0; e < plan.nB; e++) cyc_div(q, part, k1, plan.B[e], p);
@@ -121,8 +134,23 @@ cyclo_reduce_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ hol
     for (int e = 0; e < plan.nB; e++) { lt = min(n, lt + plan.B[e]); cyc_mul(t, lt, plan.B[e], p); }
     for (int e = 0; e < plan.nD; e++) cyc_div(t, part, n, plan.D[e], p);
     // ---- r = f' - t on [0, n)
+    // four coefficients per iteration: all eight global loads are issued before the first one is consumed (the
+    // one-at-a-time loop spent a third of the kernel waiting on them)
     uint32_t* o = dst + (long long)r * H;
-    for (int i = tid; i < H; i += kCycT) o[i] = i < n ? cyc_subm(fold(i), t[i], p) : 0u;
+    for (int i0 = tid; i0 < H; i0 += 4 * kCycT) {
+        uint32_t a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = i0 + u * kCycT;
+            a[u] = i < n ? f[i] : 0u;
+            b[u] = (i < n && i + m < N) ? f[i + m] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = i0 + u * kCycT;
+            if (i < H) o[i] = i < n ? cyc_subm(cyc_addm(a[u], b[u], p), t[i], p) : 0u;
+        }
+    }
 }
 
 }  // namespace cuhe_b200

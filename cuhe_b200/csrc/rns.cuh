@@ -399,7 +399,7 @@ icrt_kernel_v2(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, con
 // p / floor(2^64/p) / b_l sit in shared memory.  Same single final reduction as generation 2.  Falls back to
 // generation 2 for truncated M_l or primes >= 2^26.
 // ---------------------------------------------------------------------------
-template <int W4>
+template <int W4, bool MANY>     // MANY: more than 32 residues (several accumulate / flush rounds)
 __global__ void __launch_bounds__(128)
 icrt_kernel_v3(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, const uint32_t* __restrict__ primes,
                const uint64_t* __restrict__ mus, const uint32_t* __restrict__ M, const uint32_t* __restrict__ mi,
@@ -446,8 +446,7 @@ icrt_kernel_v3(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, con
         }
     };
     uint32_t cur = src[icrt_src_row(0, bat, L, H, grp_G, grp_nb) + idx];
-    for (int l0 = 0; l0 < L; l0 += 32) {       // at most 32 products per column sum between two flushes
-        const int l1 = min(l0 + 32, L);
+    auto mac_range = [&](int l0, int l1) {     // acc += tt_l * M_l for l in [l0, l1): at most 32 residues
         for (int l = l0; l < l1; l++) {
             const uint32_t nxt = (l + 1 < L) ? src[icrt_src_row(l + 1, bat, L, H, grp_G, grp_nb) + idx] : 0u;
             // (c mod p) * b mod p == (c * b) mod p: one reduction (c < 2^32, b < 2^26)
@@ -461,7 +460,15 @@ icrt_kernel_v3(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, con
             }
             cur = nxt;
         }
+    };
+    // up to 32 residues are one accumulate + flush with no loop around it: in the looped form the accumulators stay
+    // live across the flush and the compiler tracks their 40 halves separately (3 instructions per multiply-add)
+    if constexpr (!MANY) {
+        mac_range(0, L);
         flush();
+    } else {
+#pragma unroll 1
+        for (int l0 = 0; l0 < L; l0 += 32) { mac_range(l0, min(l0 + 32, L)); flush(); }
     }
     // S = sum < L*M.  Quotient estimate from the top three words (scaled by 2^(-32(W-2)) like m_top).
     double sd = 0.0;
