@@ -439,10 +439,13 @@ def run_ours(args):
                 "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
                 "peak_source": pk_src + " (burst copy bandwidth)", "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": NTT_BYTES_64K * cnt, "launch_ms": kms, "batch": cnt,
-                "secondary": {"bound": "instruction issue / int32 alu pipe: ~205 SASS instructions per point, ~70 % of them on the alu pipe "
-                                       "(64 lanes/clk/SM); measured issue ceiling with both pipes busy 105 thread-instr/clk/SM "
-                                       "(profiles/r02_pipe_issue_rates.txt)",
-                              "thread_instr_per_point": 205, "issue_ceiling_ntt_per_s_per_gpu": 148 * 1.965e9 * 105 / (205 * 65536)},
+                "secondary": {"bound": "int32 alu pipe: 199.5 SASS instructions per point (ncu, profiles/r02_gen4_ntt_full.txt: 56.2 M + "
+                                       "153.0 M warp instructions per 512 transforms), ~68 % of them on the alu pipe (64 lanes/clk/SM), "
+                                       "alu pipe 81 % / 79 % busy in pass 1 / pass 2; measured issue ceiling with both pipes busy "
+                                       "105 thread-instr/clk/SM (profiles/r02_pipe_issue_rates.txt)",
+                              "thread_instr_per_point": 199.5, "alu_pipe_busy_pct_ncu": [81.4, 78.6],
+                              "issue_ceiling_ntt_per_s_per_gpu": 148 * 1.965e9 * 105 / (199.5 * 65536),
+                              "alu_ceiling_ntt_per_s_per_gpu": 148 * 1.965e9 * 64 / (0.68 * 199.5 * 65536)},
                 "note": "ALU-pipe / issue bound, not HBM bound (SURVEY F9); DESIGN.md section 4.2"}
 
     # ---- e2e: host buffers, H2D + D2H inside the timed region ----
@@ -523,12 +526,12 @@ def run_ours(args):
                       "residue rows, transforms, exchange back, ICRT inside the library) -> D2H (double-buffered side streams); "
                       "byte counts are whole-job totals"}
     if world == 1:
-        # one e2e step = one call with Be = 4*B products from pinned host memory; the library pipelines
+        # one e2e step = one call with Be = 8*B products from pinned host memory; the library pipelines
         # H2D | kernels | D2H over chunks of products inside the call
-        Be = 4 * B
+        Be = 8 * B
         a_np, b_np, NBUF = S["a_np"], S["b_np"], S["nbuf"]
-        ah = torch.from_numpy(np.concatenate([a_np[i % NBUF] for i in range(4)]).view(np.int32)).pin_memory()
-        bh = torch.from_numpy(np.concatenate([b_np[i % NBUF] for i in range(4)]).view(np.int32)).pin_memory()
+        ah = torch.from_numpy(np.concatenate([a_np[i % NBUF] for i in range(8)]).view(np.int32)).pin_memory()
+        bh = torch.from_numpy(np.concatenate([b_np[i % NBUF] for i in range(8)]).view(np.int32)).pin_memory()
         oh = torch.zeros((Be, H, W), dtype=torch.int32).pin_memory()
         for _ in range(2):
             check(lib.cuhe_mul_raw_host_batch(h, p(oh), p(ah), p(bh), 0, Be, st()))
