@@ -1,10 +1,11 @@
 set -x
-CUHE_B200_LIB=$PWD/variants/p1x6/libcuhe_b200.so python tools/ntt_bench.py | cut -c1-420
-python tools/ntt_bench.py | cut -c1-420
-python tools/ntt_bench.py --sweep > gpurun_out/ntt_sweep_gen4.json; python - <<PY
+nvidia-smi topo -m 2>&1 | head -12
+python -m pytest tests/test_gpu_multi.py -x -q -m gpu 2>&1 | tail -3
+for n in 8 4; do
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $n --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_n$n.json 2> gpurun_out/bench_n$n.err; tail -c 300 gpurun_out/bench_n$n.err
+python - <<PY
 import json
-d=json.load(open('gpurun_out/ntt_sweep_gen4.json'))
-for r in d["rows"]: print(r["N"], r["batch"], round(r["fwd_ms_per_transform"]*1e3,2), "us fwd", round(r["inv_ms_per_transform"]*1e3,2), "us inv")
-print("cfg0 latency ms", d["config0_fwd_plus_inv_latency_ms"])
+d=json.loads(open('gpurun_out/bench_n$n.json').read().strip().splitlines()[-1])
+print("N=$n", {k:d.get(k) for k in ("value","ms_per_step","verified","ntt_64k_per_s")}, "e2e", d["e2e"]["value"], "c5", d["config5"])
 PY
-python bench.py --steps 10 --warmup 3 --no-cpu --no-c5 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['e2e'])"
+done
