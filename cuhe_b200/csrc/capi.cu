@@ -178,15 +178,17 @@ static void run_ntt(cuhe_ctx* c, const NttPlan& pl, int mode, int out, Pass1Args
 // forward zero-padded transform of `count` polynomials.
 //   src: u32, polynomial t at src + t*src_stride (+ offset), crtLen = N/2 words read
 //   mul_tab != null: outputs multiplied by mul_tab[t % row_mod][.]
+//   lazy: outputs are any 64-bit representative (only for results that go straight into the fused product of
+//         inv_ntt_modp, whose multiply accepts unreduced operands)
 static void fwd_ntt(cuhe_ctx* c, int N, uint64_t* dst, const uint32_t* src, long long src_stride, int count,
-                    const uint64_t* mul_tab, int row_mod, cudaStream_t st) {
+                    const uint64_t* mul_tab, int row_mod, cudaStream_t st, bool lazy = false) {
     const NttPlan& pl = get_plan(c, N);
     Pass1Args a{};
     a.src = src; a.tw1 = pl.tw1; a.src_stride = src_stride; a.n2 = pl.n2;
     Pass2Args b{};
     b.dst = dst; b.tw2 = pl.tw2; b.mul_tab = mul_tab; b.dst_stride = N;
     b.row_mod = row_mod > 0 ? row_mod : 1;
-    run_ntt(c, pl, IN_EXT_U32, mul_tab ? OUT_U64_MUL : OUT_U64, a, b, count, st);
+    run_ntt(c, pl, IN_EXT_U32, mul_tab ? OUT_U64_MUL : (lazy ? OUT_U64_LAZY : OUT_U64), a, b, count, st);
 }
 // forward transform whose zero-padded input is gathered (and optionally folded mod x^m - 1):
 // x[j] = src[t*stride + base + dir*j] (+ src[.. + fold_m] mod p), j < len
@@ -873,7 +875,7 @@ static void mul_crt_batch_impl(cuhe_ctx* c, uint32_t* dst, const uint32_t* a_raw
     do_crt(c, ca, a_raw, lvl, batch, st);
     do_crt(c, cb, b_raw, lvl, batch, st);
     uint64_t* na = nab.as<uint64_t>();
-    fwd_ntt(c, N, na, ca, H, 2 * cnt, nullptr, 1, st);          // both operands, one launch per pass
+    fwd_ntt(c, N, na, ca, H, 2 * cnt, nullptr, 1, st, true);    // both operands, one launch per pass; unreduced outputs
     intt_mod_impl(c, dst, na, na + (size_t)cnt * N, lvl, batch, st);
 }
 int cuhe_intt_mod(cuhe_ctx* c, uint32_t* dst, const uint64_t* src, int lvl, cuhe_stream stream) {
@@ -1441,7 +1443,7 @@ int cuhe_mul_raw_sharded_batch(cuhe_ctx* c, uint32_t* raw_out, const uint32_t* a
             ch[k].prod.reset(new Tmp(c, std::max<size_t>(1, (size_t)cnt * H * 4), s));
             if (cnt > 0) {
                 Tmp nab(c, (size_t)2 * cnt * N * 8, s);
-                fwd_ntt(c, N, nab.as<uint64_t>(), ch[k].ca->as<uint32_t>(), H, (int)(2 * cnt), nullptr, 1, s);
+                fwd_ntt(c, N, nab.as<uint64_t>(), ch[k].ca->as<uint32_t>(), H, (int)(2 * cnt), nullptr, 1, s, true);
                 intt_mod_impl(c, ch[k].prod->as<uint32_t>(), nab.as<uint64_t>(), nab.as<uint64_t>() + (size_t)cnt * N, lvl,
                               ch[k].nbc * G, s);
             }

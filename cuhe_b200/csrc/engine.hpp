@@ -35,7 +35,9 @@ struct Pass1Args {
 enum Pass2Out {
     OUT_U64 = 0,       // natural-order u64[N]                                (ntt_3_*)
     OUT_U64_MUL = 1,   // ... times a per-row u64[N] table                    (+barrett_mul_un/mn)
-    OUT_U32_MODP = 2   // (value % p) as u32[N]                               (intt_3_*_modcrt)
+    OUT_U32_MODP = 2,  // (value % p) as u32[N]                               (intt_3_*_modcrt)
+    OUT_U64_LAZY = 3   // natural-order u64[N], any 64-bit representative of the residue (not reduced below P):
+                       // for transforms that only feed the fused pointwise product of the inverse (IN_U64_REV_MUL)
 };
 struct Pass2Args {
     void* dst;                 // [count][dst_stride]

@@ -197,6 +197,8 @@ template <int R3, int OUT>
 L96_HD void ntt4_store_out(const Pass2Args& a, int t, int trow, int k, L96 y, uint32_t p, uint64_t mu) {
     if constexpr (OUT == OUT_U64) {
         ((uint64_t*)a.dst)[(long long)t * a.dst_stride + k] = l96_canon(y);
+    } else if constexpr (OUT == OUT_U64_LAZY) {
+        ((uint64_t*)a.dst)[(long long)t * a.dst_stride + k] = l96_fold_u64(y);
     } else if constexpr (OUT == OUT_U64_MUL) {
         const uint64_t m = ld4_nc_u64(a.mul_tab + (long long)trow * (64 * 64 * R3) + k);
 #if defined(__CUDA_ARCH__)
@@ -334,7 +336,9 @@ __global__ void __launch_bounds__(512, 3) ntt4_pass2_kernel(Pass2Args a) {
     extern __shared__ uint64_t sm4[];
     uint64_t* lo = sm4;
     uint32_t* hi = reinterpret_cast<uint32_t*>(sm4 + Cfg::ELEMS);
-    const int tid = threadIdx.x, bx = blockIdx.x, t = blockIdx.y;
+    // transforms in reverse launch order: pass 1 wrote the intermediate of the last transforms most recently, so when
+    // the whole intermediate is larger than L2 those rows are still resident (the first ones are in DRAM either way)
+    const int tid = threadIdx.x, bx = blockIdx.x, t = gridDim.y - 1 - blockIdx.y;
     ntt4_pass2_phase<R3, OUT, 0>(a, tid, bx, t, lo, hi, lo, hi);
     __syncthreads();
     ntt4_pass2_phase<R3, OUT, 1>(a, tid, bx, t, lo, hi, lo, hi);

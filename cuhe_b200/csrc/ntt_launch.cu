@@ -53,6 +53,7 @@ static cudaError_t launch4_p2_out(int out, const Pass2Args& a, int count, cudaSt
         case OUT_U64: return launch4_p2<R3, OUT_U64>(a, count, st);
         case OUT_U64_MUL: return launch4_p2<R3, OUT_U64_MUL>(a, count, st);
         case OUT_U32_MODP: return launch4_p2<R3, OUT_U32_MODP>(a, count, st);
+        case OUT_U64_LAZY: return launch4_p2<R3, OUT_U64_LAZY>(a, count, st);
     }
     return cudaErrorInvalidValue;
 }

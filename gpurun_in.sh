@@ -1,11 +1,10 @@
 set -x
-nvidia-smi topo -m 2>&1 | head -12
-python -m pytest tests/test_gpu_multi.py -x -q -m gpu 2>&1 | tail -3
-for n in 8 4; do
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $n --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_n$n.json 2> gpurun_out/bench_n$n.err; tail -c 300 gpurun_out/bench_n$n.err
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_ref_base.py -x -q -m gpu 2>&1 | tail -3
+python tools/ntt_bench.py | cut -c1-420
+python bench.py --steps 20 --warmup 3 --no-c5 > gpurun_out/bench_n1d.json 2> gpurun_out/bench_n1d.err; tail -c 300 gpurun_out/bench_n1d.err
 python - <<PY
 import json
-d=json.loads(open('gpurun_out/bench_n$n.json').read().strip().splitlines()[-1])
-print("N=$n", {k:d.get(k) for k in ("value","ms_per_step","verified","ntt_64k_per_s")}, "e2e", d["e2e"]["value"], "c5", d["config5"])
+d=json.loads(open('gpurun_out/bench_n1d.json').read().strip().splitlines()[-1])
+print({k:d.get(k) for k in ("value","ms_per_step","ntt_64k_per_s","gpu_launches")}, "e2e", d["e2e"]["value"], "traffic", d["roofline"]["traffic"], d["roofline"]["traffic_source"][:60], "cpu", d["cpu_baseline"]["value"])
 PY
-done
+ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_r02c.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-c5 > /dev/null 2>&1

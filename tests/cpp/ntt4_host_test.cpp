@@ -120,6 +120,15 @@ static void test_size() {
         run_pass2<R3, OUT_U32_MODP>(ib, 1);
         for (int j = 0; j < N; j++) CHECK(back[j] == (uint32_t)(conv[j] % prime), "product N=%d j=%d", N, j);
     }
+    // lazy outputs (OUT_U64_LAZY): same residues, not necessarily reduced below P; the fused product accepts them
+    {
+        std::vector<uint64_t> Y((size_t)2 * N);
+        Pass2Args lb = b; lb.dst = Y.data();
+        run_pass1<N2, IN_EXT_U32>(a, 2);
+        run_pass2<R3, OUT_U64>(b, 2);
+        run_pass2<R3, OUT_U64_LAZY>(lb, 2);
+        for (size_t k = 0; k < (size_t)2 * N; k++) CHECK(Y[k] % P == X[k], "lazy output N=%d k=%zu", N, k);
+    }
     // table epilogue (OUT_U64_MUL): result * tab
     {
         std::vector<uint64_t> tab(N), Y(N);
