@@ -1,10 +1,10 @@
 set -x
-python -m pytest tests/test_gpu_parity.py tests/test_gpu_ref_base.py -x -q -m gpu 2>&1 | tail -3
-python tools/ntt_bench.py | cut -c1-420
-python bench.py --steps 20 --warmup 3 --no-c5 > gpurun_out/bench_n1d.json 2> gpurun_out/bench_n1d.err; tail -c 300 gpurun_out/bench_n1d.err
+timeout 300 python tools/ntt_bench.py | cut -c1-330
+CUHE_B200_NTT_FUSED=8 CUHE_B200_NTT_FUSED_CHUNK=4 timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "ntt or mul or relin" 2>&1 | tail -3
+timeout 300 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --cache-control none -k regex:ntt4_ -s 4 -c 3 --csv --log-file gpurun_out/ncu_fused_dram.csv python tools/ntt_bench.py --one > /dev/null 2>&1
 python - <<PY
-import json
-d=json.loads(open('gpurun_out/bench_n1d.json').read().strip().splitlines()[-1])
-print({k:d.get(k) for k in ("value","ms_per_step","ntt_64k_per_s","gpu_launches")}, "e2e", d["e2e"]["value"], "traffic", d["roofline"]["traffic"], d["roofline"]["traffic_source"][:60], "cpu", d["cpu_baseline"]["value"])
+import csv
+rows=[r for r in csv.reader(open('gpurun_out/ncu_fused_dram.csv')) if len(r)>5]
+h=next(r for r in rows if "Kernel Name" in r)
+for r in rows[rows.index(h)+1:]: print(r[h.index("Kernel Name")][:40], r[h.index("Metric Name")], r[h.index("Metric Value")], r[h.index("Metric Unit")])
 PY
-ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_r02c.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-c5 > /dev/null 2>&1
