@@ -543,6 +543,9 @@ def run_ours(args):
         el = time.perf_counter() - t0
         e2e = {"value": Be * args.steps / el, "unit": "mul/s", "h2d_bytes_per_step": int(2 * Be * S["n"] * W * 4),
                "d2h_bytes_per_step": int(Be * S["n"] * W * 4), "batch": Be,
+               "h2d_GBps": 2 * Be * S["n"] * W * 4 * args.steps / el / 1e9,
+               "pcie_ceiling_note": "tools/pcie_bw.py on the same box: pinned H2D 55.6 GB/s alone, 50.0 GB/s with D2H running",
+
                "api": "cuhe_mul_raw_host_batch (pinned host RAW in/out, 3-stream pipeline inside the call; only the modLen "
                       "coefficient rows of a ring element cross PCIe, the zero rows up to crtLen do not)"}
         del ah, bh, oh
