@@ -427,7 +427,8 @@ static void do_icrt(cuhe_ctx* c, uint32_t* raw_out, const uint32_t* crt_all, int
 }
 // generation 3 (padded word count a template constant): W <= 64 and every prime below 2^26
 template <int W4>
-static void launch_crt_v3_w(cuhe_ctx* c, uint32_t* dst, const uint32_t* raw, PrimeView pv, int rows, int W, int batch, cudaStream_t st) {
+static void launch_crt_v3_w(cuhe_ctx* c, uint32_t* dst, const uint32_t* raw, PrimeView pv, int rows, int W, int batch, cudaStream_t st,
+                            int grp_G) {
     static bool done[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -436,15 +437,16 @@ static void launch_crt_v3_w(cuhe_ctx* c, uint32_t* dst, const uint32_t* raw, Pri
         done[dev] = true;
     }
     const int H = c->par.crtLen;
-    const size_t smem = (size_t)(((rows * W4 + rows + 1) & ~1)) * 4 + (size_t)rows * 8;
+    const size_t smem = (size_t)(((rows * W4 + rows + 1) & ~1)) * 4 + (size_t)rows * 16;
     dim3 grid((H + 127) / 128, batch);
-    crt_kernel_v3<W4><<<grid, 128, smem, st>>>(dst, raw, pv, rows, c->d_pow32, c->pow_stride, W, c->par.modLen, H);
+    crt_kernel_v3<W4><<<grid, 128, smem, st>>>(dst, raw, pv, rows, c->d_pow32, c->pow_stride, W, c->par.modLen, H, grp_G, batch);
     count_launch();
 }
-static bool launch_crt_v3(cuhe_ctx* c, uint32_t* dst, const uint32_t* raw, PrimeView pv, int rows, int W, int batch, cudaStream_t st) {
+static bool launch_crt_v3(cuhe_ctx* c, uint32_t* dst, const uint32_t* raw, PrimeView pv, int rows, int W, int batch, cudaStream_t st,
+                          int grp_G = 0) {
     if (W > 64) return false;           // (every CRT prime is below 2^26, checked at context creation: 16 products per 64-bit sum)
     switch ((W + 3) / 4) {
-#define CRT3(q) case q: launch_crt_v3_w<4 * q>(c, dst, raw, pv, rows, W, batch, st); return true;
+#define CRT3(q) case q: launch_crt_v3_w<4 * q>(c, dst, raw, pv, rows, W, batch, st, grp_G); return true;
         CRT3(1) CRT3(2) CRT3(3) CRT3(4) CRT3(5) CRT3(6) CRT3(7) CRT3(8) CRT3(9) CRT3(10) CRT3(11) CRT3(12) CRT3(13) CRT3(14) CRT3(15) CRT3(16)
 #undef CRT3
     }
@@ -1424,10 +1426,14 @@ int cuhe_mul_raw_sharded_batch(cuhe_ctx* c, uint32_t* raw_out, const uint32_t* a
             uint32_t* snd[2] = {ch[k].send->as<uint32_t>(), ch[k].send->as<uint32_t>() + (size_t)nbc * L * H};
             uint32_t* rcv[2] = {ch[k].ca->as<uint32_t>(), ch[k].ca->as<uint32_t>() + (size_t)Bc * rows_me * H};
             const uint32_t* raws[2] = {a_raw + (size_t)ch[k].b0 * H * W, b_raw + (size_t)ch[k].b0 * H * W};
-            for (int op = 0; op < 2; op++)
+            for (int op = 0; op < 2; op++) {
+                // one launch writes the residues of all L primes straight into the grouped send layout; the per-peer
+                // launches (a coefficient's words loaded G times) remain for word counts generation 3 does not cover
+                if (launch_crt_v3(c, snd[op], raws[op], PrimeView{c->d_primes, c->d_mus, 0, 1}, L, W, nbc, s, G)) { CK(cudaGetLastError()); continue; }
                 for (int j = 0; j < G; j++)
                     do_crt_view(c, snd[op] + (size_t)nbc * pre(j) * H, raws[op], PrimeView{c->d_primes, c->d_mus, j, G}, rows_of(j),
                                 lvl, nbc, s);
+            }
             NK(api->GroupStart());
             for (int op = 0; op < 2; op++)
                 for (int j = 0; j < G; j++) {

@@ -185,19 +185,26 @@ crt_kernel_v2(uint32_t* __restrict__ dst, const uint32_t* __restrict__ raw, Prim
 template <int W4>
 __global__ void __launch_bounds__(128)
 crt_kernel_v3(uint32_t* __restrict__ dst, const uint32_t* __restrict__ raw, PrimeView pv, int rows,
-              const uint32_t* __restrict__ pow32, int pow_stride, int W, int n, int H) {   // dst: [batch][rows][H]
+              const uint32_t* __restrict__ pow32, int pow_stride, int W, int n, int H, int grp_G, int grp_nb) {
+    // dst: [batch][rows][H], or (grp_G > 1, all primes) the grouped layout of icrt_src_row: rows of rank j's primes
+    // of all grp_nb polynomials back to back -- what the sharded multiply sends to rank j in one piece
     static_assert(W4 % 4 == 0 && W4 >= 4, "padded word count must be a multiple of 4");
-    extern __shared__ uint32_t sh[];          // [rows][W4] powers, [rows] p, [rows] mu (u64, 8-byte aligned)
+    extern __shared__ uint32_t sh[];          // [rows][W4] powers, [rows] p, [rows] mu, [rows] row offset (u64, 8-byte aligned)
     uint32_t* spw = sh;
     uint32_t* sp = sh + rows * W4;
     uint64_t* smu = reinterpret_cast<uint64_t*>(sh + ((rows * W4 + rows + 1) & ~1));
+    long long* soff = reinterpret_cast<long long*>(smu + rows);
     for (int e = threadIdx.x; e < rows * W4; e += 128) {
         const int r = e / W4, k = e - r * W4;                     // W4 is a constant: multiply-shift
         spw[e] = k < W ? pow32[(long long)prime_index(pv, r) * pow_stride + k] : 0u;
     }
-    for (int r = threadIdx.x; r < rows; r += 128) { const int l = prime_index(pv, r); sp[r] = pv.p[l]; smu[r] = pv.mu[l]; }
+    const int bat = blockIdx.y;
+    for (int r = threadIdx.x; r < rows; r += 128) {
+        const int l = prime_index(pv, r);
+        sp[r] = pv.p[l]; smu[r] = pv.mu[l];
+        soff[r] = icrt_src_row(r, bat, rows, H, grp_G, grp_nb);
+    }
     const int i = blockIdx.x * 128 + threadIdx.x;
-    dst += (long long)blockIdx.y * rows * H;
     uint32_t c[W4];
     {   // every thread loads (index clamped into the polynomial; words >= W are zero): leaving c[] undefined for
         // the threads past n makes the compiler carry every word as a 64-bit value, 3 instructions per multiply-add
@@ -216,7 +223,7 @@ crt_kernel_v3(uint32_t* __restrict__ dst, const uint32_t* __restrict__ raw, Prim
     }
     __syncthreads();
     if (i >= n) {
-        if (i < H) for (int r = 0; r < rows; r++) dst[(long long)r * H + i] = 0;
+        if (i < H) for (int r = 0; r < rows; r++) dst[soff[r] + i] = 0;
         return;
     }
 #pragma unroll 2
@@ -234,7 +241,7 @@ crt_kernel_v3(uint32_t* __restrict__ dst, const uint32_t* __restrict__ raw, Prim
                 part = mod_u64_u32(a0 + a1 + part, p, mu); a0 = a1 = 0;
             }
         }
-        dst[(long long)r * H + i] = mod_u64_u32(a0 + a1 + part, p, mu);
+        dst[soff[r] + i] = mod_u64_u32(a0 + a1 + part, p, mu);
     }
 }
 
