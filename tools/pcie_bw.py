@@ -1,10 +1,12 @@
 #!/usr/bin/env python
 """Pinned-memory PCIe bandwidth of the box: H2D alone, D2H alone, both at once (two streams) -- the ceiling of every
-end-to-end (`e2e`) number in bench.py.  python tools/pcie_bw.py"""
+end-to-end (`e2e`) number in bench.py.  python tools/pcie_bw.py [device]; start one process per GPU at the same
+time to see what the host side sustains in aggregate (the `e2e` ceiling at N > 1)."""
 import json
+import sys
 import torch
 
-dev = torch.device("cuda", 0)
+dev = torch.device("cuda", int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 n = 1 << 28                                   # 1 GiB of int32
 h_in = torch.empty(n, dtype=torch.int32).pin_memory()
 h_out = torch.empty(n, dtype=torch.int32).pin_memory()
@@ -41,5 +43,5 @@ def both():
 
 gb = n * 4 / 1e9
 s1.wait_stream(torch.cuda.current_stream()); s2.wait_stream(torch.cuda.current_stream())
-print(json.dumps({"h2d_GBps": gb / timed(h2d) * 1e3, "d2h_GBps": gb / timed(d2h) * 1e3,
+print(json.dumps({"device": dev.index, "h2d_GBps": gb / timed(h2d) * 1e3, "d2h_GBps": gb / timed(d2h) * 1e3,
                   "both_GBps_each_direction": gb / timed(both) * 1e3}))
