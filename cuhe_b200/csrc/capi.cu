@@ -775,7 +775,25 @@ int cuhe_memcpy(cuhe_ctx* c, void* dst, const void* src, size_t bytes, int kind,
         REQUIRE(c && (bytes == 0 || (dst && src)), "null argument"); REQUIRE(kind >= 0 && kind <= 2, "bad copy kind");
         DeviceGuard dg(c->device);
         const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : (kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice);
-        if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, k, (cudaStream_t)stream));
+        if (!bytes) return;
+        if (kind == 2) {
+            // device to device across two GPUs (moveTo / copyTo, cuhe/CuHE.cu:217-257): blocks of one device's memory
+            // pool are not mapped on the other, so a plain cudaMemcpyAsync fails with "invalid argument"; the peer
+            // copy works with or without peer access
+            cudaPointerAttributes ad{}, as{};
+            CK(cudaPointerGetAttributes(&ad, dst));
+            CK(cudaPointerGetAttributes(&as, src));
+            if (ad.type == cudaMemoryTypeDevice && as.type == cudaMemoryTypeDevice && ad.device != as.device) {
+                if (cudaMemcpyPeerAsync(dst, ad.device, src, as.device, bytes, (cudaStream_t)stream) == cudaSuccess) return;
+                cudaGetLastError();                       // no peer path for these blocks: stage through the host
+                std::vector<unsigned char> tmp(bytes);
+                CK(cudaStreamSynchronize((cudaStream_t)stream));
+                { DeviceGuard gs(as.device); CK(cudaMemcpy(tmp.data(), src, bytes, cudaMemcpyDeviceToHost)); }
+                { DeviceGuard gd(ad.device); CK(cudaMemcpy(dst, tmp.data(), bytes, cudaMemcpyHostToDevice)); }
+                return;
+            }
+        }
+        CK(cudaMemcpyAsync(dst, src, bytes, k, (cudaStream_t)stream));
     });
 }
 int cuhe_memset(cuhe_ctx* c, void* ptr, int value, size_t bytes, cuhe_stream stream) {

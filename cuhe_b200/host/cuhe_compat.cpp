@@ -423,16 +423,19 @@ void moveTo(CuCtxt& tar, int dstDev, cudaStream_t st) {     // cuhe/CuHE.cu:217-
     if (dstDev == tar.device()) return;
     void* p = nullptr;
     const int srcDev = tar.device();
+    // the destination block comes from the other device's pool on ITS default stream; the copy runs on a stream of the
+    // source device, so the allocation is synchronised first (each domain below: allocate, sync, peer copy, sync)
+    auto alloc_dst = [&](size_t bytes) { ok(cuhe_malloc(ctx(dstDev), &p, bytes, nullptr)); ok(cuhe_stream_sync(ctx(dstDev), nullptr)); };
     if (tar.domain() == 1) {
-        ok(cuhe_malloc(ctx(dstDev), &p, tar.rRepSize(), nullptr));
+        alloc_dst(tar.rRepSize());
         d2d(srcDev, p, tar.rRep(), tar.rRepSize(), st); ok(cuhe_stream_sync(ctx(srcDev), st));
         tar.rRepFree(); tar.rRep((uint32*)p);
     } else if (tar.domain() == 2) {
-        ok(cuhe_malloc(ctx(dstDev), &p, tar.cRepSize(), nullptr));
+        alloc_dst(tar.cRepSize());
         d2d(srcDev, p, tar.cRep(), tar.cRepSize(), st); ok(cuhe_stream_sync(ctx(srcDev), st));
         tar.cRepFree(); tar.cRep((uint32*)p);
     } else if (tar.domain() == 3) {
-        ok(cuhe_malloc(ctx(dstDev), &p, tar.nRepSize(), nullptr));
+        alloc_dst(tar.nRepSize());
         d2d(srcDev, p, tar.nRep(), tar.nRepSize(), st); ok(cuhe_stream_sync(ctx(srcDev), st));
         tar.nRepFree(); tar.nRep((uint64*)p);
     }

@@ -1,4 +1,1 @@
-set -x
-python tools/pcie_bw.py 0
-python tools/pcie_bw.py 1
-python tools/pcie_bw.py 0 & python tools/pcie_bw.py 1 & wait
+python -m pytest tests/test_gpu_multi.py -x -q -m gpu 2>&1 | tail -3

@@ -50,7 +50,7 @@ static void on_crash(int sig) {
 }
 #define STEP(msg) do { std::printf("step: %s\n", msg); std::fflush(stdout); } while (0)
 
-int main() {
+int main(int argc, char** argv) {
     std::signal(SIGSEGV, on_crash);
     std::signal(SIGABRT, on_crash);
     std::setvbuf(stdout, nullptr, _IONBF, 0);
@@ -162,6 +162,43 @@ int main() {
     }
     STEP("relin");
     resetParameters();
+    // ---- two devices in ONE process, the reference's own multi-GPU semantics (cuhe/DeviceManager.cu:50-70,
+    //      cuhe/CuHE.cu:217-257): run as `compat_test twodev` on a box with two GPUs (tests/test_gpu_multi.py) ----
+    if (argc > 1 && std::string(argv[1]) == "twodev") {
+        setParameters(5, 2, 1, 61, 20, 8191);
+        multiGPUs(2);
+        EXPECT(numGPUs() == 2);
+        std::vector<ZZ> cm3((size_t)param.depth);
+        initCuHE(cm3.data(), phi);                      // tables on both devices
+        ZZX a3, b3;
+        SetCoeff(a3, 0, rand_below(cm3[0], seed)); SetCoeff(a3, 5, rand_below(cm3[0], seed)); SetCoeff(a3, n - 1, rand_below(cm3[0], seed));
+        for (int i = 0; i < n; i++) SetCoeff(b3, i, rand_below(cm3[0], seed));
+        const ZZX want = mul_mod_ref(a3, b3, m, cm3[0]);
+        {   // (ciphertexts release their device blocks before resetParameters drops the contexts)
+        CuCtxt x, y, z;
+        x.setLevel(0, 0, a3); y.setLevel(0, 0, b3);
+        x.x2c();
+        copyTo(z, x, 1);                                // CRT domain, device 0 -> 1
+        EXPECT(z.device() == 1 && x.device() == 0 && z.domain() == 2);
+        y.x2n();
+        moveTo(y, 1);                                   // NTT domain, moved as it is
+        EXPECT(y.device() == 1 && y.domain() == 3);
+        z.x2n();                                        // device 1 transforms with its own tables
+        cAnd(z, z, y);
+        z.x2z();
+        EXPECT(z.zRep() == want);
+        moveTo(y, 0);
+        x.x2n();
+        cAnd(x, x, y);
+        x.x2z();
+        EXPECT(x.zRep() == want);
+        ZZX got;
+        mulZZX(got, a3, b3, 0, 1);                      // mulZZX(..., dev = 1)
+        EXPECT(got == want);
+        }
+        STEP("two devices: copyTo / moveTo / products on device 1");
+        resetParameters();
+    }
     if (fails == 0) std::printf("compat ok\n");
     return fails ? 1 : 0;
 }
