@@ -147,8 +147,7 @@ L96_HD void ntt4_pass1_phase(const Pass1Args& a, int tid, int bx, int t, uint64_
 #pragma unroll
             for (int k = 4; k < 8; k++) x[k] = L96{0, 0, 0};
         }
-        l96_dif<8, EXT, INB>(x);                              // over k -> a = bitrev3(r)
-        l96_twiddle8_dyn<ABITS, FOLD0>(x, i);                 // * 2^(3*i*a); i is the warp index
+        l96_dif8_tw_dyn<EXT, INB, FOLD0>(x, i);               // over k -> a = bitrev3(r), * 2^(3*i*a); i is the warp index
 #pragma unroll
         for (int r = 0; r < 8; r++) st4(s_lo, s_hi, (l96_bitrev(r, 3) * 8 + i) * C + lane, x[r]);
     } else {
@@ -245,8 +244,7 @@ L96_HD void ntt4_pass2_phase(const Pass2Args& a, int tid, int bx, int t, uint64_
             L96 x[8];
 #pragma unroll
             for (int k = 0; k < 8; k++) x[k] = l96_mul(xv[k], wv[k]);
-            l96_dif<8, false, kL96MulOutBits>(x);
-            l96_twiddle8_dyn<ABITS, FOLD0>(x, wi);
+            l96_dif8_tw_dyn<false, kL96MulOutBits, FOLD0>(x, wi);   // radix 8 over k -> a, * 2^(3*i*a)
             uint64_t* blo = e1_lo + (row * RS1L + wi * R3 + j2b);
             uint32_t* bhi = e1_hi + (row * RS1H + wi * R3 + j2b);
 #pragma unroll
@@ -281,16 +279,18 @@ L96_HD void ntt4_pass2_phase(const Pass2Args& a, int tid, int bx, int t, uint64_
             const int row = u % R, k2a = u / R;
             const int base = k2a * R + row;
             L96 y[8];
+            constexpr int SB = kL96MulOutBits + 1;
+            // first radix-2 stage of the 16-point block: h = 0 keeps the sums, h = 1 the differences times
+            // w16^m = 2^(12m); for 32 < 12m < 96 as 2^(12m+96) (hi - lo): the cheaper far-side fold, sign for free
 #pragma unroll
             for (int m = 0; m < 8; m++) {
                 const L96 lo = ld4(e2_lo, e2_hi, base + m * PS), hi = ld4(e2_lo, e2_hi, base + (m + 8) * PS);
-                y[m] = h ? l96_sub(lo, hi) : l96_add(lo, hi);
+                y[m] = h ? ((12 * m > 32 && 12 * m < 96) ? l96_sub(hi, lo) : l96_sub(lo, hi)) : l96_add(lo, hi);
             }
-            constexpr int SB = kL96MulOutBits + 1;
-            if (h) {                                           // * w16^m = 2^(12m)
-                y[1] = l96_shl<12, SB>(y[1]); y[2] = l96_shl<24, SB>(y[2]); y[3] = l96_shl<36, SB>(y[3]);
-                y[4] = l96_shl<48, SB>(y[4]); y[5] = l96_shl<60, SB>(y[5]); y[6] = l96_shl<72, SB>(y[6]);
-                y[7] = l96_shl<84, SB>(y[7]);
+            if (h) {
+                y[1] = l96_shl<12, SB>(y[1]); y[2] = l96_shl<24, SB>(y[2]); y[3] = l96_shl<36 + 96, SB>(y[3]);
+                y[4] = l96_shl<48 + 96, SB>(y[4]); y[5] = l96_shl<60 + 96, SB>(y[5]); y[6] = l96_shl<72 + 96, SB>(y[6]);
+                y[7] = l96_shl<84 + 96, SB>(y[7]);
             }
             static_assert(l96_dif_bits(8, false, SB) <= kL96FoldInBits, "fold bound");
             l96_dif<8, false, SB>(y);

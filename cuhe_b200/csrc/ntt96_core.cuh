@@ -102,4 +102,42 @@ L96_HD void l96_twiddle8_dyn(L96 (&x)[8], int i) {
 }
 L96_HD constexpr int l96_twiddle8_bits(int bits, bool fold0) { return fold0 ? kL96ShlOutBits : l96_max(bits, kL96ShlOutBits); }
 
+// 8-point DIF transform fused with the inter-layer twiddle 2^(3*I*bitrev3(r)): the first two stages as in l96_dif,
+// the last stage (sum / difference, no twiddle of its own) together with the twiddle, so that a difference whose
+// twiddle exponent lies in (32, 96) is formed the other way round and shifted by s + 96 (2^96 == -1: the cheaper
+// far-side fold, sign for free).  Same outputs as l96_dif<8> followed by l96_twiddle8<I>.
+template <int I, int BITS, bool FOLD0, int M>
+L96_HD void l96_last_stage_tw(L96 (&x)[8]) {
+    constexpr int r0 = 2 * M, r1 = 2 * M + 1;
+    constexpr int s0 = (3 * I * l96_bitrev(r0, 3)) % 192, s1 = (3 * I * l96_bitrev(r1, 3)) % 192;
+    const L96 a = x[r0], b = x[r1];
+    x[r0] = l96_twiddle_one<s0, BITS + 1, FOLD0>(l96_add(a, b));
+    if constexpr (s1 > 32 && s1 < 96) x[r1] = l96_shl<s1 + 96, BITS + 1>(l96_sub(b, a));
+    else x[r1] = l96_twiddle_one<s1, BITS + 1, FOLD0>(l96_sub(a, b));
+}
+template <int I, bool HALF_INPUT, int BITS, bool FOLD0>
+L96_HD void l96_dif8_tw(L96 (&x)[8]) {
+    constexpr int B1 = HALF_INPUT ? l96_max(BITS, kL96ShlOutBits) : l96_stage_bits(BITS);     // after stage H = 4
+    constexpr int B2 = l96_stage_bits(B1);                                                    // after stage H = 2
+    static_assert(B2 + 1 <= 94, "butterfly sums would leave the 96-bit window");
+    l96_stage<8, 4, HALF_INPUT, BITS>(x, std::make_integer_sequence<int, 4>{});
+    l96_stage<8, 2, false, B1>(x, std::make_integer_sequence<int, 4>{});
+    l96_last_stage_tw<I, B2, FOLD0, 0>(x); l96_last_stage_tw<I, B2, FOLD0, 1>(x);
+    l96_last_stage_tw<I, B2, FOLD0, 2>(x); l96_last_stage_tw<I, B2, FOLD0, 3>(x);
+}
+// i is uniform across the warp
+template <bool HALF_INPUT, int BITS, bool FOLD0>
+L96_HD void l96_dif8_tw_dyn(L96 (&x)[8], int i) {
+    switch (i) {
+        case 0: l96_dif8_tw<0, HALF_INPUT, BITS, FOLD0>(x); break;
+        case 1: l96_dif8_tw<1, HALF_INPUT, BITS, FOLD0>(x); break;
+        case 2: l96_dif8_tw<2, HALF_INPUT, BITS, FOLD0>(x); break;
+        case 3: l96_dif8_tw<3, HALF_INPUT, BITS, FOLD0>(x); break;
+        case 4: l96_dif8_tw<4, HALF_INPUT, BITS, FOLD0>(x); break;
+        case 5: l96_dif8_tw<5, HALF_INPUT, BITS, FOLD0>(x); break;
+        case 6: l96_dif8_tw<6, HALF_INPUT, BITS, FOLD0>(x); break;
+        default: l96_dif8_tw<7, HALF_INPUT, BITS, FOLD0>(x); break;
+    }
+}
+
 }  // namespace cuhe_b200
