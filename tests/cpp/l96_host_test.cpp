@@ -84,6 +84,30 @@ static void test_tw() {
 template <int BITS, bool FOLD0, int... I>
 static void test_tw_all(std::integer_sequence<int, I...>) { (test_tw<I, BITS, FOLD0>(), ...); }
 
+// the fused block the pass kernels use (last radix-8 stage together with the inter-layer twiddle, far-side shifts for
+// the differences) against the definition: X[bitrev3(r)] * 2^(3*I*bitrev3(r)), and against its stated magnitude
+template <int I, bool HALF, int BITS, bool FOLD0>
+static void test_dif8_tw() {
+    const uint64_t w = powP(2, 24);
+    constexpr int OUTB = l96_twiddle8_bits(l96_dif_bits(8, HALF, BITS), FOLD0);
+    for (int it = 0; it < 200; it++) {
+        L96 x[8]; uint64_t in[8];
+        for (int i = 0; i < 8; i++) { x[i] = (HALF && i >= 4) ? L96{0, 0, 0} : rnd(BITS); in[i] = modP(l96_val(x[i])); }
+        if (it == 0) for (int i = 0; i < (HALF ? 4 : 8); i++) x[i] = l96_make(((i & 1) ? -1 : 1) * (((i128)1 << BITS) - 1)), in[i] = modP(l96_val(x[i]));
+        l96_dif8_tw_dyn<HALF, BITS, FOLD0>(x, I);
+        for (int r = 0; r < 8; r++) {
+            const int a = l96_bitrev(r, 3);
+            uint64_t want = 0;
+            for (int j = 0; j < 8; j++) want = (uint64_t)(((u128)want + mulP(in[j], powP(w, (uint64_t)j * a))) % P);
+            want = mulP(want, powP(2, (3 * I * a) % 192));
+            CHECK(modP(l96_val(x[r])) == want, "dif8_tw<%d,%d,%d> output %d", I, (int)HALF, BITS, r);
+            CHECK(below(x[r], OUTB), "dif8_tw<%d,%d,%d,%d> magnitude of output %d", I, (int)HALF, BITS, (int)FOLD0, r);
+        }
+    }
+}
+template <bool HALF, int BITS, bool FOLD0, int... I>
+static void test_dif8_tw_all(std::integer_sequence<int, I...>) { (test_dif8_tw<I, HALF, BITS, FOLD0>(), ...); }
+
 int main() {
     // add / sub / from
     for (int it = 0; it < 2000; it++) {
@@ -127,6 +151,10 @@ int main() {
     test_tw_all<68, false>(std::make_integer_sequence<int, 8>{});
     test_tw_all<70, true>(std::make_integer_sequence<int, 8>{});
     test_tw_all<72, true>(std::make_integer_sequence<int, 8>{});
+    // the fused blocks exactly as the kernels instantiate them: pass 1 (zero-padded u32; u64; product) and pass 2
+    test_dif8_tw_all<true, 32, false>(std::make_integer_sequence<int, 8>{});
+    test_dif8_tw_all<false, 64, false>(std::make_integer_sequence<int, 8>{});
+    test_dif8_tw_all<false, 67, true>(std::make_integer_sequence<int, 8>{});
     printf("l96 host test: %d failures, %d window overflows\n", g_fail, g_overflow);
     return (g_fail || g_overflow) ? 1 : 0;
 }
