@@ -8,7 +8,7 @@
 // (pass 2) resident warps per SM, 80 registers in pass 2, an instruction-issue rate of 54 % of peak.  Here
 // EVERY THREAD OWNS EIGHT POINTS and the radix-8 layers exchange through a CTA-wide shared tile:
 //   pass 1  CTA = 32 columns x 64 rows, 256 threads; warp w transforms rows {w + 8k} (layer A), then rows
-//           {8w + i} of the tile (layer B); 24 KB of shared memory, 6 CTAs = 48 warps per SM
+//           {8w + i} of the tile (layer B); 24 KB of shared memory, 5-6 CTAs = 40-48 warps per SM
 //   pass 2  CTA = 4096 points (64/R3 rows), 512 threads: layer A1 (x table w^(k1 j2), radix 8), layer A2
 //           (radix 8, x table w_N2^(k2a j2b)), layer B (R3-point; for R3 = 16 as two half-blocks of eight so
 //           that no thread ever holds more than eight values); 49 KB, 2-3 CTAs = 32-48 warps per SM
