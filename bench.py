@@ -588,6 +588,10 @@ def run_ours(args):
         # the table the reference publishes (doc/Perf_NTT.txt): per-transform time for N x batch, and the
         # configs[0] latency.  Isolated in a child process so that nothing it does can disturb this line.
         sweep = child_json("ntt_bench.py", "--sweep")
+    # BASELINE configs[3]: homomorphic PRINCE end to end against the reference's known answer (tools/prince_bench.py)
+    prince = None
+    if rank == 0 and world == 1 and not args.no_cpu and not args.no_prince:
+        prince = child_json("prince_bench.py")
 
     # ---- the reference interface itself: cuHE::mulZZX (ZZX in, ZZX out; cuhe/CuHE.cu:259-268) through libcuhe_compat.so,
     #      one call per product, host threads on their own streams (tools/mulzzx_bench.cpp, child process) ----
@@ -615,7 +619,7 @@ def run_ours(args):
                        "parallelism": f"residue-shard x{world}: every rank owns {args.batch} products, residue rows exchanged by NCCL send/recv "
                                       "inside cuhe_mul_raw_sharded_batch" if world > 1 else "single GPU",
                        "l2": f"{S['nbuf']} rotating operand sets; per-step NTT intermediates {2 * B * L * N * 8 / world / 1e6:.0f} MB per GPU exceed the 126 MB L2"},
-            "verified": verified, "ntt_64k_per_s": ntt_rate, "ntt_sweep": sweep, "relin_config3": relin3, "config5": config5,
+            "verified": verified, "ntt_64k_per_s": ntt_rate, "ntt_sweep": sweep, "relin_config3": relin3, "prince_config4": prince, "config5": config5,
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "e2e_mulzzx": mulzzx, "gpu_launches": launches, "clocks": clocks,
         }
         print(json.dumps(out))
@@ -632,6 +636,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=32, help="ciphertext pairs per step and per GPU (32: 9.0 k mul/s, 8: 7.9 k)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-prince", action="store_true", help="skip the homomorphic PRINCE child (BASELINE configs[3], ~40 s)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / relin / sweep / live ncu traffic legs")
     ap.add_argument("--no-c5", action="store_true", help="skip the BASELINE configs[4] leg (64 primes)")
     args = ap.parse_args()
